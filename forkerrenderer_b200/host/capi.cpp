@@ -1,0 +1,155 @@
+// capi.cpp — C entry points over the C++ facade, for ctypes (tests, bench.py) and other FFI callers.
+// These are conveniences above the real boundary (include/forkergl_b200.h): load a .scene with the facade's
+// loaders, run Render::Preconfigure + Render::Render, hand out the fgl context for plane reads.
+#include <unistd.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "forkergl.h"
+#include "forkergl_b200.h"
+#include "output.h"
+#include "render.h"
+#include "shadow.h"
+
+static std::string s_Error;
+
+template <typename F>
+static int Guard(F&& f)
+{
+    try
+    {
+        f();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        s_Error = e.what();
+        return 1;
+    }
+}
+
+extern "C" {
+
+const char* frh_last_error() { return s_Error.c_str(); }
+
+fgl_ctx* frh_context()
+{
+    fgl_ctx* c = nullptr;
+    Guard([&] { c = ForkerGL::Context(); });
+    return c;
+}
+
+void frh_shutdown() { ForkerGL::Shutdown(); }
+
+// Loads a .scene.  Model paths inside it are relative to assets_dir (the reference resolves them against the
+// CWD; we chdir for the duration of the load).  wrap/filter are the ForkerGL texture modes in force while the
+// textures load (reference model.cpp:425).
+int frh_scene_load(const char* assets_dir, const char* scene_file, int wrap, int filter, void** out_scene)
+{
+    return Guard([&] {
+        char cwd[4096];
+        if (!getcwd(cwd, sizeof cwd)) throw std::runtime_error("getcwd failed");
+        std::string scenePath = scene_file;
+        if (scenePath.empty() || scenePath[0] != '/') scenePath = std::string(cwd) + "/" + scenePath;
+        if (assets_dir && *assets_dir && chdir(assets_dir) != 0)
+            throw std::runtime_error(std::string("cannot chdir to ") + assets_dir);
+        ForkerGL::TextureWrapMode((Texture::WrapMode)wrap);
+        ForkerGL::TextureFilterMode((Texture::FilterMode)filter);
+        Scene* s = nullptr;
+        try
+        {
+            s = new Scene(scenePath);
+        }
+        catch (...)
+        {
+            if (chdir(cwd) != 0) {}
+            throw;
+        }
+        if (chdir(cwd) != 0) {}
+        if (!s->IsValid())
+        {
+            delete s;
+            throw std::runtime_error(std::string("failed to load scene ") + scene_file);
+        }
+        for (unsigned i = 0; i < s->GetModelCount(); ++i) s->GetModel(i).UploadToDevice();
+        *out_scene = s;
+    });
+}
+
+void frh_scene_free(void* scene) { delete (Scene*)scene; }
+
+// info[0..7] = width, height, ssaa on, ssaa k, ssao on, deferred, shadow on, triangle count
+int frh_scene_info(void* scene, int* info)
+{
+    return Guard([&] {
+        Scene* s = (Scene*)scene;
+        int    tris = 0;
+        for (unsigned i = 0; i < s->GetModelCount(); ++i) tris += s->GetModel(i).GetNumFaces();
+        info[0] = s->GetWidth(), info[1] = s->GetHeight(), info[2] = s->IsSSAAOn(), info[3] = s->GetSSAAKernelSize();
+        info[4] = s->IsSSAOOn(), info[5] = ForkerGL::GetRenderMode() == ForkerGL::Deferred;
+        info[6] = Shadow::GetShadowStatus(), info[7] = tris;
+    });
+}
+
+int frh_set_camera(void* scene, const float eye[3], const float look_at[3])
+{
+    return Guard([&] {
+        Scene* s = (Scene*)scene;
+        s->GetCamera().SetPosition(eye[0], eye[1], eye[2]);
+        s->GetCamera().SetLookAtPos(look_at[0], look_at[1], look_at[2]);
+    });
+}
+
+// One frame: Render::Preconfigure + Render::Render (reference main.cpp:37-40).
+int frh_render(void* scene, int shadow_mode, int materialize_frame_f32)
+{
+    return Guard([&] {
+        Scene* s = (Scene*)scene;
+        Shadow::SetShadowMode((Shadow::Mode)shadow_mode);
+        ForkerGL::Params().materialize_frame_f32 = materialize_frame_f32;
+        Render::Preconfigure(*s);
+        Render::Render(*s);
+    });
+}
+
+// Output::* of the reference's main (main.cpp:43-52) into `dir`.
+int frh_output_tga(const char* dir)
+{
+    return Guard([&] {
+        Output::SetDirectory(dir);
+        Output::OutputFrameBuffer();
+        Output::OutputSSAAImage();
+        Output::OutputShadowBuffer();
+        Output::OutputZBuffer();
+        if (ForkerGL::GetRenderMode() == ForkerGL::Deferred)
+        {
+            Output::OutputNormalGBuffer();
+            Output::OutputWorldPosGBuffer();
+            Output::OutputAlbedoGBuffer();
+            Output::OutputParamGBuffer();
+            Output::OutputShadingTypeGBuffer();
+            Output::OutputAmbientOcclusionGBuffer();
+        }
+    });
+}
+
+// Host matrix builders, for the bit-exactness test against the reference's (tests/test_host_math.py).
+// out = model(16) normal(9) lookat(16) persp(16) ortho(16) ortho*lookat(16)
+void frh_test_matrices(const float t[3], float rot, float scale, const float eye[3], const float center[3],
+                       float ratio, float* out)
+{
+    Matrix4x4f M = MakeModelMatrix(Vector3f(t[0], t[1], t[2]), rot, scale);
+    Matrix3x3f N = MakeNormalMatrix(M);
+    Matrix4x4f L = MakeLookAtMatrix(Vector3f(eye[0], eye[1], eye[2]), Vector3f(center[0], center[1], center[2]));
+    Matrix4x4f P = MakePerspectiveMatrix(45.f, ratio, 0.01f, 20.f);
+    Matrix4x4f O = MakeOrthographicMatrix(-3 * ratio, 3 * ratio, -3, 3, 0.1f, 20.f);
+    Matrix4x4f OL = O * L;
+    int        k = 0;
+    auto put4 = [&](const Matrix4x4f& m) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[k++] = m[r][c]; };
+    put4(M);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) out[k++] = N[r][c];
+    put4(L), put4(P), put4(O), put4(OL);
+}
+}  // extern "C"

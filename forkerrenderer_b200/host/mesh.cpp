@@ -1,0 +1,37 @@
+// mesh.cpp — Mesh accessors and the draw-call site (reference src/mesh.cpp:10-61).
+#include "mesh.h"
+
+#include "forkergl.h"
+#include "model.h"
+#include "shader.h"
+
+// Reference Mesh::Draw (mesh.cpp:10-25): per face { shader.Use; 3x ProcessVertex; ForkerGL::DrawTriangle }.
+// Here: one indexed draw of all faces, executed by the device vertex/raster kernels.
+void Mesh::Draw(Shader& shader) const
+{
+    shader.Use(shared_from_this());
+    ForkerGL::DrawMesh(*this, shader);
+}
+
+Vector3f Mesh::Vert(int faceIdx, int vertIdx) const
+{
+    return m_Model.GetVert(m_FaceVertIndices[faceIdx * 3 + vertIdx]);
+}
+Vector2f Mesh::TexCoord(int faceIdx, int vertIdx) const
+{
+    return m_Model.GetTexCoord(m_FaceTexCoordIndices[faceIdx * 3 + vertIdx]);
+}
+Vector3f Mesh::Normal(int faceIdx, int vertIdx) const
+{
+    return Normalize(m_Model.GetNormal(m_FaceNormalIndices[faceIdx * 3 + vertIdx]));
+}
+Vector3f Mesh::Tangent(int faceIdx, int vertIdx) const
+{
+    return Normalize(m_Model.GetTangent(m_FaceTangentIndices[faceIdx * 3 + vertIdx]));
+}
+
+int Mesh::DeviceId() const
+{
+    if (m_DeviceId < 0) m_Model.UploadToDevice();
+    return m_DeviceId;
+}
