@@ -1,0 +1,814 @@
+// api.cu — the C ABI of include/forkergl_b200.h over the CUDA kernels: context, resources, ForkerGL state, pass
+// flushing, plane I/O and instrumentation.  This library has no CPU path: every entry either enqueues device work
+// on the context's stream or fails with an error code.
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <map>
+
+#include "fgl_internal.h"
+#include "stream.h"
+
+static std::string g_createError;
+
+int fgl_fail(fgl_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->error = msg;
+    else g_createError = msg;
+    return code;
+}
+
+int fgl_reserve(fgl_ctx* c, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return FGL_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    void*  p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess)
+    {
+        cudaGetLastError();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return fgl_fail(c, FGL_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+        want = bytes;
+    }
+    if (b.p)
+    {   // growth keeps the contents (a pass can be flushed more than once)
+        cudaMemcpyAsync(p, b.p, b.cap, cudaMemcpyDeviceToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(b.p);
+    }
+    b.p = p, b.cap = want;
+    return FGL_OK;
+}
+
+static void release(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr, b.cap = 0;
+}
+
+void fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes)
+{
+    TimingRec r;
+    r.name = name, r.bytes = bytes;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, c->stream);
+    c->timings.push_back(r);
+}
+void fgl_time_end(fgl_ctx* c) { cudaEventRecord(c->timings.back().e1, c->stream); }
+
+namespace
+{
+#define ENTER(c)                                                      \
+    if (!(c)) return FGL_ERR_INVALID;                                 \
+    if (cudaSetDevice((c)->device) != cudaSuccess) return fgl_fail((c), FGL_ERR_CUDA, "cudaSetDevice failed")
+
+void identity(float* m)
+{
+    memset(m, 0, 16 * sizeof(float));
+    m[0] = m[5] = m[10] = m[15] = 1.f;
+}
+
+bool is1ch(int plane) { return plane == FGL_PLANE_DEPTH || plane == FGL_PLANE_SHADOW || plane == FGL_PLANE_SHADINGTYPE || plane == FGL_PLANE_AO; }
+
+int plane_init(fgl_ctx* c, int plane, int w, int h, float value)
+{
+    if (w <= 0 || h <= 0 || w > 65535 || h > 65535) return fgl_fail(c, FGL_ERR_INVALID, "buffer size out of range");
+    PlaneH& p = c->planes[plane];
+    p.w = w, p.h = h, p.ch = is1ch(plane) ? 1 : 3;
+    if (int rc = fgl_reserve(c, p.buf, (size_t)w * h * p.ch * 4)) return rc;
+    p.fillPending = true, p.fillValue = value, p.fillIsRGB = false;
+    return FGL_OK;
+}
+
+// executes a deferred clear (Buffer constructors of the reference, buffer.cpp:8-18,101-111)
+int materialize(fgl_ctx* c, int plane)
+{
+    PlaneH& p = c->planes[plane];
+    if (!p.fillPending || !p.buf.p) return FGL_OK;
+    p.fillPending = false;
+    size_t n = (size_t)p.w * p.h;
+    if (p.fillIsRGB) return fgl_run_fill_rgb(c, (float*)p.buf.p, n, p.fillRGB);
+    return fgl_run_fill(c, (float*)p.buf.p, n * p.ch, p.fillValue);
+}
+
+void band_of(fgl_ctx* c, int H, int& r0, int& r1)
+{
+    r0 = std::max(0, std::min(c->row0, H));
+    r1 = c->row1 < 0 ? H : std::max(r0, std::min(c->row1, H));
+}
+
+PlanesD planes_dev(fgl_ctx* c)
+{
+    PlanesD d;
+    for (int i = 0; i <= FGL_PLANE_AO; ++i) d.p[i] = (float*)c->planes[i].buf.p;
+    return d;
+}
+
+int upload_tex_table(fgl_ctx* c)
+{
+    if (!c->texTableDirty) return FGL_OK;
+    std::vector<TexD> t(std::max<size_t>(1, c->textures.size()));
+    for (size_t i = 0; i < c->textures.size(); ++i) t[i] = c->textures[i].desc;
+    if (int rc = fgl_reserve(c, c->texTable, t.size() * sizeof(TexD))) return rc;
+    FGL_CUDA(c, cudaMemcpyAsync(c->texTable.p, t.data(), t.size() * sizeof(TexD), cudaMemcpyHostToDevice, c->stream));
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->texTableDirty = false;
+    return FGL_OK;
+}
+
+ShadowMapD shadow_map_dev(fgl_ctx* c)
+{
+    ShadowMapD   s;
+    const PlaneH& p = c->planes[FGL_PLANE_SHADOW];
+    s.d = (const float*)p.buf.p, s.w = p.w, s.h = p.h;
+    s.iw = (int)((float)p.w - 0.001f), s.ih = (int)((float)p.h - 0.001f);  // shadow.cpp:27-28
+    return s;
+}
+
+void fill_light_consts(fgl_ctx* c, LightPass& L)
+{
+    L.shadowOn = c->shadowOn, L.shadowMode = c->params.shadow_mode;
+    L.biasSlope = c->params.shadow_bias_slope, L.biasMin = c->params.shadow_bias_min;
+    L.shadowIntensity = c->params.shadow_intensity, L.areaLight = c->params.area_light_size;
+    L.pcfFilter = c->params.pcf_filter_size, L.pcssFilter = c->params.pcss_blocker_filter_size;
+    L.disk = nullptr, L.chunkOf = nullptr, L.useAO = 1;
+    L.writeF32 = c->params.materialize_frame_f32;
+}
+
+// Rasterises the triangles submitted since the last flush and resolves the pass into its planes.
+int flush(fgl_ctx* c)
+{
+    if (c->primCounter == c->flushedPrims) return FGL_OK;
+    bool          shadowPass = c->pass == FGL_PASS_SHADOW;
+    const PlaneH& target = c->planes[shadowPass ? FGL_PLANE_SHADOW : FGL_PLANE_DEPTH];
+    const PlaneH& depth = c->planes[FGL_PLANE_DEPTH];
+    if (!target.buf.p || !depth.buf.p || depth.w != target.w || depth.h != target.h)
+    {
+        c->flushedPrims = c->primCounter;
+        return fgl_fail(c, FGL_ERR_STATE, "draw without matching Init*Buffer calls (the reference would index out of bounds)");
+    }
+    RasterPass P;
+    memset(&P, 0, sizeof P);
+    P.W = target.w, P.H = target.h;
+    P.row0 = 0, P.row1 = P.H;
+    if (!shadowPass) band_of(c, P.H, P.row0, P.row1);
+    P.passType = c->pass, P.shadowOn = c->shadowOn;
+    memcpy(P.viewport, c->viewport, sizeof P.viewport);
+    size_t  nPix = (size_t)P.W * P.H;
+    DevBuf& vis = shadowPass ? c->visLight : c->visCamera;
+    bool&   visClear = shadowPass ? c->visLightClear : c->visCamClear;
+    int&    vw = shadowPass ? c->visLightW : c->visCamW;
+    int&    vh = shadowPass ? c->visLightH : c->visCamH;
+    // InitDepthBuffer (forkergl.cpp:60-63) re-creates the depth buffer the NEXT raster pass tests against
+    if (c->depthInitPending) visClear = true, c->depthInitPending = false;
+    if (vw != P.W || vh != P.H) visClear = true;
+    if (int rc = fgl_reserve(c, vis, nPix * 8)) return rc;
+    vw = P.W, vh = P.H;
+    if (visClear)
+    {
+        ++c->launches;
+        if (c->timing) fgl_time_begin(c, "vis_clear", nPix * 8);
+        FGL_CUDA(c, cudaMemsetAsync(vis.p, 0xFF, nPix * 8, c->stream));
+        if (c->timing) fgl_time_end(c);
+        visClear = false;
+    }
+    int nPrims = c->primCounter, nNew = nPrims - c->flushedPrims;
+    if (int rc = fgl_reserve(c, c->drawsDev, c->draws.size() * sizeof(DrawCmdD))) return rc;
+    FGL_CUDA(c, cudaMemcpyAsync(c->drawsDev.p, c->draws.data(), c->draws.size() * sizeof(DrawCmdD), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = fgl_reserve(c, c->setup, (size_t)nPrims * sizeof(TriSetup))) return rc;
+    if (shadowPass) { if (int rc = fgl_reserve(c, c->zndc, (size_t)nPrims * sizeof(float4))) return rc; }
+    else if (int rc = fgl_reserve(c, c->vary, (size_t)nPrims * sizeof(TriVary))) return rc;
+    if (int rc = fgl_reserve(c, c->nblk, ((size_t)nPrims + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, c->blkScan, ((size_t)nNew + 1) * 4)) return rc;
+    FGL_CUDA(c, cudaMemsetAsync((int*)c->nblk.p + nPrims, 0, 4, c->stream));
+    if (int rc = upload_tex_table(c)) return rc;
+    P.draws = (const DrawCmdD*)c->drawsDev.p, P.nDraws = (int)c->draws.size(), P.nPrims = nPrims;
+    P.setup = (TriSetup*)c->setup.p, P.vary = (TriVary*)c->vary.p, P.zndc = (float4*)c->zndc.p;
+    P.nblk = (int*)c->nblk.p, P.blkScan = (int*)c->blkScan.p;
+    P.vis = (unsigned long long*)vis.p;
+    P.textures = (const TexD*)c->texTable.p;
+
+    bool      fullBand = P.row0 == 0 && P.row1 == P.H;
+    LightPass L;
+    memset(&L, 0, sizeof L);
+    if (shadowPass)
+    {
+        c->planes[FGL_PLANE_SHADOW].fillPending = false;
+        c->planes[FGL_PLANE_DEPTH].fillPending = false;
+    }
+    else if (c->pass == FGL_PASS_GEOMETRY)
+    {
+        static const int written[] = { FGL_PLANE_DEPTH, FGL_PLANE_NORMAL, FGL_PLANE_WORLDPOS, FGL_PLANE_LIGHTNDC, FGL_PLANE_ALBEDO,
+                                       FGL_PLANE_EMISSIVE, FGL_PLANE_PARAM, FGL_PLANE_SHADINGTYPE, FGL_PLANE_AO };
+        for (int pl : written)
+        {
+            if (pl == FGL_PLANE_LIGHTNDC && !c->shadowOn) continue;
+            const PlaneH& q = c->planes[pl];
+            if (!q.buf.p || q.w != P.W || q.h != P.H)
+            {
+                c->flushedPrims = c->primCounter;
+                return fgl_fail(c, FGL_ERR_STATE, "geometry pass without InitGeometryBuffers of the depth buffer's size");
+            }
+            if (fullBand) c->planes[pl].fillPending = false;
+            else if (int rc = materialize(c, pl)) return rc;
+        }
+    }
+    else if (c->pass == FGL_PASS_FORWARD)
+    {
+        const PlaneH& f = c->planes[FGL_PLANE_FRAME];
+        if (!f.buf.p || f.w != P.W || f.h != P.H)
+        {
+            c->flushedPrims = c->primCounter;
+            return fgl_fail(c, FGL_ERR_STATE, "forward pass without InitFrameBuffer of the depth buffer's size");
+        }
+        if (int rc = materialize(c, FGL_PLANE_FRAME)) return rc;
+        if (fullBand) c->planes[FGL_PLANE_DEPTH].fillPending = false;
+        else if (int rc = materialize(c, FGL_PLANE_DEPTH)) return rc;
+        if (c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD)
+        {
+            c->flushedPrims = c->primCounter;
+            return fgl_fail(c, FGL_ERR_UNSUPPORTED, "forward mode with PCF/PCSS needs per-fragment stream ordinals (not built yet); use FGL_SHADOW_HARD");
+        }
+        fill_light_consts(c, L);
+        if (c->shadowOn)
+        {
+            if (!c->planes[FGL_PLANE_SHADOW].buf.p)
+            {
+                c->flushedPrims = c->primCounter;
+                return fgl_fail(c, FGL_ERR_STATE, "shadows are on but no shadow pass has run");
+            }
+            if (int rc = materialize(c, FGL_PLANE_SHADOW)) return rc;
+            L.sm = shadow_map_dev(c);
+        }
+    }
+    else
+    {   // LightingPass: the reference's DrawTriangle would skip the depth test and run no program; nothing to draw
+        c->flushedPrims = c->primCounter;
+        return FGL_OK;
+    }
+    int rc = fgl_run_raster(c, P, planes_dev(c), nullptr, &L);
+    c->flushedPrims = c->primCounter;
+    c->frameRgb8Valid = false;
+    return rc;
+}
+
+int ensure_rgb8(fgl_ctx* c)
+{
+    if (c->frameRgb8Valid) return FGL_OK;
+    PlaneH& f = c->planes[FGL_PLANE_FRAME];
+    if (!f.buf.p) return fgl_fail(c, FGL_ERR_STATE, "no frame buffer");
+    if (int rc = materialize(c, FGL_PLANE_FRAME)) return rc;
+    size_t n = (size_t)f.w * f.h;
+    if (int rc = fgl_reserve(c, c->frameRgb8, n * 3 + 16)) return rc;
+    if (int rc = fgl_run_quantize(c, (const float*)f.buf.p, n, (uint8_t*)c->frameRgb8.p)) return rc;
+    c->frameRgb8Valid = true;
+    return FGL_OK;
+}
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+void fgl_default_params(FglParams* p)
+{
+    p->shadow_mode = FGL_SHADOW_PCSS;
+    p->pcf_filter_size = 0.007;
+    p->pcss_blocker_filter_size = 0.005;
+    p->area_light_size = 2.5f;
+    p->shadow_bias_slope = 0.009f;
+    p->shadow_bias_min = 0.007f;
+    p->shadow_intensity = 0.6f;
+    p->ssao_radius = 0.075f;
+    p->ssao_range_check_radius = 0.01f;
+    p->ssao_bias = 0.0005f;
+    p->ssao_range_check = 1;
+    p->materialize_frame_f32 = 1;
+}
+
+int fgl_create(int device, fgl_ctx** out)
+{
+    if (!out) return fgl_fail(nullptr, FGL_ERR_INVALID, "out_ctx is NULL");
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fgl_fail(nullptr, FGL_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fgl_fail(nullptr, FGL_ERR_INVALID, "cuda_device out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fgl_fail(nullptr, FGL_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10)
+        return fgl_fail(nullptr, FGL_ERR_UNSUPPORTED, std::string("device ") + prop.name + " is not sm_100a (kernels are built for Blackwell only)");
+    fgl_ctx* c = new fgl_ctx();
+    c->device = device;
+    if ((e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking)) != cudaSuccess)
+    {
+        delete c;
+        return fgl_fail(nullptr, FGL_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    c->stream = c->ownStream;
+    fgl_default_params(&c->params);
+    identity(c->viewport), identity(c->viewProj), identity(c->lightSpace);
+    *out = c;
+    return FGL_OK;
+}
+
+void fgl_destroy(fgl_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    fgl_stream_destroy(c);
+    for (auto& p : c->planes) release(p.buf);
+    release(c->frameRgb8), release(c->ssaaRgb8), release(c->visCamera), release(c->visLight), release(c->texTable);
+    release(c->drawsDev), release(c->setup), release(c->vary), release(c->zndc), release(c->nblk), release(c->blkScan), release(c->scanTmp);
+    for (auto& t : c->textures) release(t.data);
+    for (auto& v : c->vertices) release(v.pos), release(v.uv), release(v.nrm), release(v.tan);
+    for (auto& m : c->meshes) release(m.pi), release(m.ti), release(m.ni);
+    for (auto& t : c->timings) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+    cudaStreamDestroy(c->ownStream);
+    delete c;
+}
+
+const char* fgl_last_error(fgl_ctx* c) { return c ? c->error.c_str() : g_createError.c_str(); }
+const char* fgl_backend_name(void) { return "cuda-sm_100a"; }
+
+int fgl_set_stream(fgl_ctx* c, void* s)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->ownStream;
+    return FGL_OK;
+}
+int fgl_set_params(fgl_ctx* c, const FglParams* p)
+{
+    ENTER(c);
+    if (!p) return fgl_fail(c, FGL_ERR_INVALID, "params is NULL");
+    if (p->shadow_mode < FGL_SHADOW_HARD || p->shadow_mode > FGL_SHADOW_PCSS) return fgl_fail(c, FGL_ERR_INVALID, "bad shadow_mode");
+    if (int rc = flush(c)) return rc;
+    c->params = *p;
+    return FGL_OK;
+}
+int fgl_sync(fgl_ctx* c)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+
+// ---- resources ---------------------------------------------------------------------------------------------------
+static int upload(fgl_ctx* c, DevBuf& b, const void* src, size_t bytes)
+{
+    if (int rc = fgl_reserve(c, b, std::max<size_t>(bytes, 16))) return rc;
+    if (bytes) FGL_CUDA(c, cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return FGL_OK;
+}
+
+int fgl_upload_texture(fgl_ctx* c, const uint8_t* texels, int w, int h, int bpp, int wrap, int filter, int* id)
+{
+    ENTER(c);
+    if (!texels || w <= 0 || h <= 0 || (bpp != 1 && bpp != 3 && bpp != 4) || !id || wrap < 0 || wrap > 3 || filter < 0 || filter > 1)
+        return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_texture: bad arguments");
+    TextureH t;
+    if (int rc = upload(c, t.data, texels, (size_t)w * h * bpp)) return rc;
+    t.desc.data = (const uint8_t*)t.data.p, t.desc.w = w, t.desc.h = h, t.desc.bpp = bpp, t.desc.wrap = wrap, t.desc.filter = filter;
+    c->textures.push_back(t);
+    c->texTableDirty = true;
+    *id = (int)c->textures.size() - 1;
+    return FGL_OK;
+}
+
+int fgl_upload_vertices(fgl_ctx* c, const float* pos, int np, const float* uv, int nt, const float* nrm, int nn, const float* tan, int ntan, int* id)
+{
+    ENTER(c);
+    if (!id || np < 0 || nt < 0 || nn < 0 || ntan < 0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_vertices: bad arguments");
+    VerticesH v;
+    v.nPos = pos ? np : 0, v.nUv = uv ? nt : 0, v.nNrm = nrm ? nn : 0, v.nTan = tan ? ntan : 0;
+    if (int rc = upload(c, v.pos, pos, (size_t)v.nPos * 12)) return rc;
+    if (int rc = upload(c, v.uv, uv, (size_t)v.nUv * 8)) return rc;
+    if (int rc = upload(c, v.nrm, nrm, (size_t)v.nNrm * 12)) return rc;
+    if (int rc = upload(c, v.tan, tan, (size_t)v.nTan * 12)) return rc;
+    c->vertices.push_back(v);
+    *id = (int)c->vertices.size() - 1;
+    return FGL_OK;
+}
+
+int fgl_upload_mesh(fgl_ctx* c, int vid, int nFaces, const int* pi, const int* ti, const int* ni, const FglMaterial* mat, int hasTangents,
+                    int supportPBR, int* id)
+{
+    ENTER(c);
+    if (!id || !mat || vid < 0 || vid >= (int)c->vertices.size() || nFaces < 0 || (nFaces && (!pi || !ti || !ni)))
+        return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_mesh: bad arguments");
+    const VerticesH& vb = c->vertices[vid];
+    if (hasTangents && vb.nTan == 0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_mesh: has_tangents without tangents");
+    for (int i = 0; i < nFaces * 3; ++i)
+        if (pi[i] < 0 || pi[i] >= vb.nPos || ti[i] < 0 || ti[i] >= vb.nUv || ni[i] < 0 || ni[i] >= vb.nNrm || (hasTangents && pi[i] >= vb.nTan))
+            return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_mesh: index out of range");
+    const int maps[] = { mat->diffuse_map, mat->specular_map, mat->normal_map, mat->emissive_map, mat->base_color_map, mat->roughness_map,
+                         mat->metalness_map, mat->ao_map, mat->pbr_normal_map, mat->pbr_emissive_map };
+    for (int t : maps)
+        if (t >= (int)c->textures.size()) return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_mesh: texture id out of range");
+    MeshH m;
+    m.vertices = vid, m.nFaces = nFaces, m.mat = *mat, m.hasTangents = hasTangents ? 1 : 0, m.supportPBR = supportPBR ? 1 : 0;
+    if (int rc = upload(c, m.pi, pi, (size_t)nFaces * 12)) return rc;
+    if (int rc = upload(c, m.ti, ti, (size_t)nFaces * 12)) return rc;
+    if (int rc = upload(c, m.ni, ni, (size_t)nFaces * 12)) return rc;
+    c->meshes.push_back(m);
+    *id = (int)c->meshes.size() - 1;
+    return FGL_OK;
+}
+
+// ---- ForkerGL state --------------------------------------------------------------------------------------------------
+int fgl_init_frame_buffer(fgl_ctx* c, int w, int h)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    c->frameRgb8Valid = false;
+    return plane_init(c, FGL_PLANE_FRAME, w, h, 0.f);
+}
+int fgl_init_depth_buffer(fgl_ctx* c, int w, int h)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    c->depthInitPending = true;
+    return plane_init(c, FGL_PLANE_DEPTH, w, h, FLT_MAX);
+}
+int fgl_init_shadow_buffer(fgl_ctx* c, int w, int h)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    return plane_init(c, FGL_PLANE_SHADOW, w, h, 0.f);
+}
+int fgl_init_geometry_buffers(fgl_ctx* c, int w, int h)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    static const int zero[] = { FGL_PLANE_NORMAL, FGL_PLANE_WORLDPOS, FGL_PLANE_ALBEDO, FGL_PLANE_EMISSIVE, FGL_PLANE_PARAM, FGL_PLANE_SHADINGTYPE };
+    for (int pl : zero)
+        if (int rc = plane_init(c, pl, w, h, 0.f)) return rc;
+    if (c->shadowOn)
+        if (int rc = plane_init(c, FGL_PLANE_LIGHTNDC, w, h, 0.f)) return rc;
+    return plane_init(c, FGL_PLANE_AO, w, h, 1.f);
+}
+int fgl_clear_color(fgl_ctx* c, const float rgb[3])
+{
+    ENTER(c);
+    if (!rgb) return fgl_fail(c, FGL_ERR_INVALID, "rgb is NULL");
+    if (int rc = flush(c)) return rc;
+    PlaneH& f = c->planes[FGL_PLANE_FRAME];
+    if (!f.buf.p) return fgl_fail(c, FGL_ERR_STATE, "ClearColor before InitFrameBuffer");
+    f.fillPending = true, f.fillIsRGB = true;
+    memcpy(f.fillRGB, rgb, 12);
+    c->frameRgb8Valid = false;
+    return FGL_OK;
+}
+int fgl_set_viewport(fgl_ctx* c, int x, int y, int w, int h)  // forkergl.cpp:89-102
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    identity(c->viewport);
+    c->viewport[0] = w / 2.f;
+    c->viewport[5] = h / 2.f;
+    c->viewport[3] = x + w / 2.f;
+    c->viewport[7] = y + h / 2.f;
+    c->viewport[10] = 1 / 2.f;
+    c->viewport[11] = 1 / 2.f;
+    return FGL_OK;
+}
+int fgl_get_viewport_matrix(fgl_ctx* c, float o[16]) { ENTER(c); memcpy(o, c->viewport, 64); return FGL_OK; }
+int fgl_set_view_projection_matrix(fgl_ctx* c, const float m[16]) { ENTER(c); memcpy(c->viewProj, m, 64); return FGL_OK; }
+int fgl_get_view_projection_matrix(fgl_ctx* c, float o[16]) { ENTER(c); memcpy(o, c->viewProj, 64); return FGL_OK; }
+int fgl_set_light_space_matrix(fgl_ctx* c, const float m[16]) { ENTER(c); memcpy(c->lightSpace, m, 64); return FGL_OK; }
+int fgl_get_light_space_matrix(fgl_ctx* c, float o[16]) { ENTER(c); memcpy(o, c->lightSpace, 64); return FGL_OK; }
+int fgl_set_render_mode(fgl_ctx* c, int mode)
+{
+    ENTER(c);
+    if (mode != FGL_MODE_FORWARD && mode != FGL_MODE_DEFERRED) return fgl_fail(c, FGL_ERR_INVALID, "bad render mode");
+    c->mode = mode;
+    return FGL_OK;
+}
+int fgl_get_render_mode(fgl_ctx* c, int* mode) { ENTER(c); *mode = c->mode; return FGL_OK; }
+int fgl_set_pass_type(fgl_ctx* c, int pass)
+{
+    ENTER(c);
+    if (pass < FGL_PASS_FORWARD || pass > FGL_PASS_SHADOW) return fgl_fail(c, FGL_ERR_INVALID, "bad pass type");
+    if (int rc = flush(c)) return rc;
+    c->pass = pass;
+    c->primCounter = c->flushedPrims = 0;
+    c->draws.clear();
+    return FGL_OK;
+}
+int fgl_set_shadow_status(fgl_ctx* c, int on)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    c->shadowOn = on ? 1 : 0;
+    return FGL_OK;
+}
+int fgl_begin_frame(fgl_ctx* c)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    fgl_stream_begin_frame(c);
+    return FGL_OK;
+}
+int fgl_set_row_band(fgl_ctx* c, int row0, int row1)
+{
+    ENTER(c);
+    if (row0 < 0 || (row1 >= 0 && row1 < row0)) return fgl_fail(c, FGL_ERR_INVALID, "bad row band");
+    if (int rc = flush(c)) return rc;
+    c->row0 = row0, c->row1 = row1;
+    return FGL_OK;
+}
+
+// ---- draws -----------------------------------------------------------------------------------------------------------
+int fgl_draw_mesh(fgl_ctx* c, int meshId, int kind, const FglUniforms* un)
+{
+    ENTER(c);
+    if (!un || meshId < 0 || meshId >= (int)c->meshes.size()) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_mesh: bad mesh");
+    if (kind < FGL_SHADER_DEPTH || kind > FGL_SHADER_PBR) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_mesh: bad shader kind");
+    if (c->pass == FGL_PASS_GEOMETRY && kind != FGL_SHADER_G)
+        return fgl_fail(c, FGL_ERR_STATE, "geometry pass requires GShader (reference forkergl.cpp:214 dynamic_cast)");
+    if (c->pass == FGL_PASS_SHADOW && kind != FGL_SHADER_DEPTH) return fgl_fail(c, FGL_ERR_STATE, "shadow pass requires DepthShader");
+    if (c->pass == FGL_PASS_FORWARD && kind != FGL_SHADER_BLINN_PHONG && kind != FGL_SHADER_PBR)
+        return fgl_fail(c, FGL_ERR_STATE, "forward pass requires BlinnPhongShader or PBRShader");
+    const MeshH& m = c->meshes[meshId];
+    if (m.nFaces == 0) return FGL_OK;
+    if ((long long)c->primCounter + m.nFaces > 0x7fffffffLL) return fgl_fail(c, FGL_ERR_INVALID, "too many triangles in one pass");
+    const VerticesH& vb = c->vertices[m.vertices];
+    DrawCmdD         d;
+    memset(&d, 0, sizeof d);
+    d.pos = (const float*)vb.pos.p, d.uv = (const float*)vb.uv.p, d.nrm = (const float*)vb.nrm.p, d.tan = (const float*)vb.tan.p;
+    d.pi = (const int*)m.pi.p, d.ti = (const int*)m.ti.p, d.ni = (const int*)m.ni.p;
+    d.mat = m.mat, d.hasTangents = m.hasTangents, d.supportPBR = m.supportPBR, d.kind = kind;
+    d.firstPrim = c->primCounter, d.nFaces = m.nFaces;
+    memcpy(d.model, un->model, 64), memcpy(d.view, un->view, 64), memcpy(d.proj, un->projection, 64);
+    memcpy(d.normal, un->normal, 36), memcpy(d.lightSpace, un->light_space, 64);
+    memcpy(d.lightPos, un->light_position, 12), memcpy(d.lightColor, un->light_color, 12), memcpy(d.eye, un->eye_position, 12);
+    for (int i = 0; i < 4; ++i)  // uLightSpaceMatrix * uModelMatrix (depthshader.h:23-24): Dot(row, column), geometry.h:784-793
+        for (int j = 0; j < 4; ++j)
+        {
+            float r = 0.f;
+            for (int k = 0; k < 4; ++k) r += un->light_space[i * 4 + k] * un->model[k * 4 + j];
+            d.lm[i * 4 + j] = r;
+        }
+    c->draws.push_back(d);
+    c->primCounter += m.nFaces;
+    return FGL_OK;
+}
+
+int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3])
+{
+    ENTER(c);
+    if (!eye || !lpos || !lcol) return fgl_fail(c, FGL_ERR_INVALID, "NULL argument");
+    if (int rc = flush(c)) return rc;
+    PlaneH& frame = c->planes[FGL_PLANE_FRAME];
+    if (!frame.buf.p) return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels before InitFrameBuffer");
+    static const int inputs[] = { FGL_PLANE_NORMAL, FGL_PLANE_WORLDPOS, FGL_PLANE_ALBEDO, FGL_PLANE_EMISSIVE, FGL_PLANE_PARAM, FGL_PLANE_SHADINGTYPE, FGL_PLANE_AO };
+    for (int pl : inputs)
+    {
+        const PlaneH& q = c->planes[pl];
+        if (!q.buf.p || q.w != frame.w || q.h != frame.h) return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels: G-buffers missing or of another size");
+        if (int rc = materialize(c, pl)) return rc;
+    }
+    LightPass L;
+    memset(&L, 0, sizeof L);
+    L.W = frame.w, L.H = frame.h;
+    band_of(c, L.H, L.row0, L.row1);
+    fill_light_consts(c, L);
+    if (c->shadowOn)
+    {
+        const PlaneH& q = c->planes[FGL_PLANE_LIGHTNDC];
+        if (!q.buf.p || q.w != frame.w || q.h != frame.h || !c->planes[FGL_PLANE_SHADOW].buf.p)
+            return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels: shadows on without LightSpaceNDCPosGBuffer / ShadowBuffer");
+        if (int rc = materialize(c, FGL_PLANE_LIGHTNDC)) return rc;
+        if (int rc = materialize(c, FGL_PLANE_SHADOW)) return rc;
+        L.sm = shadow_map_dev(c);
+    }
+    memcpy(L.eye, eye, 12), memcpy(L.lightPos, lpos, 12), memcpy(L.lightColor, lcol, 12);
+    bool fullBand = L.row0 == 0 && L.row1 == L.H;
+    if (L.writeF32)
+    {
+        if (fullBand) frame.fillPending = false;
+        else if (int rc = materialize(c, FGL_PLANE_FRAME)) return rc;
+    }
+    L.planes = planes_dev(c);
+    size_t n = (size_t)L.W * L.H;
+    if (int rc = fgl_reserve(c, c->frameRgb8, n * 3 + 16)) return rc;
+    L.rgb8 = (uint8_t*)c->frameRgb8.p;
+    if (c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD)
+        if (int rc = fgl_stream_prepare_lighting(c, L)) return rc;
+    if (int rc = fgl_run_lighting(c, L)) return rc;
+    c->frameRgb8Valid = fullBand;  // with a partial band only the band rows are current; readers take rows of the band
+    c->bandRgb8Valid = true;
+    return FGL_OK;
+}
+
+int fgl_ssao(fgl_ctx* c)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    const PlaneH& frame = c->planes[FGL_PLANE_FRAME];
+    const PlaneH& dp = c->planes[FGL_PLANE_DEPTH];
+    if (!frame.buf.p || !dp.buf.p) return fgl_fail(c, FGL_ERR_STATE, "SSAO before InitFrameBuffer / InitDepthBuffer");
+    static const int inputs[] = { FGL_PLANE_NORMAL, FGL_PLANE_WORLDPOS, FGL_PLANE_DEPTH, FGL_PLANE_AO };
+    for (int pl : inputs)
+    {
+        const PlaneH& q = c->planes[pl];
+        if (!q.buf.p || q.w != frame.w || q.h != frame.h) return fgl_fail(c, FGL_ERR_STATE, "SSAO: G-buffers missing or of another size");
+        if (int rc = materialize(c, pl)) return rc;
+    }
+    SsaoPass S;
+    memset(&S, 0, sizeof S);
+    S.W = frame.w, S.H = frame.h;
+    band_of(c, S.H, S.row0, S.row1);
+    S.worldpos = (const float*)c->planes[FGL_PLANE_WORLDPOS].buf.p, S.normal = (const float*)c->planes[FGL_PLANE_NORMAL].buf.p;
+    S.depth = (const float*)dp.buf.p, S.ao = (float*)c->planes[FGL_PLANE_AO].buf.p;
+    memcpy(S.viewProj, c->viewProj, 64), memcpy(S.viewport, c->viewport, 64);
+    S.radius = c->params.ssao_radius, S.rangeCheckRadius = c->params.ssao_range_check_radius, S.bias = c->params.ssao_bias;
+    S.rangeCheck = c->params.ssao_range_check;
+    if (int rc = fgl_stream_prepare_ssao(c, S)) return rc;
+    return fgl_run_ssao(c, S);
+}
+
+int fgl_blur(fgl_ctx* c, int plane, int kind)
+{
+    ENTER(c);
+    if (plane < 0 || plane > FGL_PLANE_AO) return fgl_fail(c, FGL_ERR_INVALID, "fgl_blur: not an fp32 plane");
+    if (int rc = flush(c)) return rc;
+    PlaneH& p = c->planes[plane];
+    if (!p.buf.p) return fgl_fail(c, FGL_ERR_STATE, "fgl_blur: plane not initialised");
+    if (int rc = materialize(c, plane)) return rc;
+    if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = false;
+    return fgl_run_blur(c, (float*)p.buf.p, p.w, p.h, p.ch, kind);
+}
+
+int fgl_ssaa_resolve(fgl_ctx* c, int k)
+{
+    ENTER(c);
+    if (k < 1) return fgl_fail(c, FGL_ERR_INVALID, "fgl_ssaa_resolve: kernel size < 1");
+    if (int rc = flush(c)) return rc;
+    const PlaneH& f = c->planes[FGL_PLANE_FRAME];
+    if (!f.buf.p) return fgl_fail(c, FGL_ERR_STATE, "SSAA before InitFrameBuffer");
+    int r0, r1;
+    band_of(c, f.h, r0, r1);
+    bool fullBand = r0 == 0 && r1 == f.h;
+    if (!(c->frameRgb8Valid || (!fullBand && c->bandRgb8Valid)))
+        if (int rc = ensure_rgb8(c)) return rc;
+    int ow = f.w / k, oh = f.h / k;
+    c->ssaaW = ow, c->ssaaH = oh;
+    if (int rc = fgl_reserve(c, c->ssaaRgb8, (size_t)ow * oh * 3 + 16)) return rc;
+    return fgl_run_ssaa(c, (const uint8_t*)c->frameRgb8.p, f.w, f.h, k, (uint8_t*)c->ssaaRgb8.p, r0, std::min(r1, oh * k));
+}
+
+// ---- buffers ---------------------------------------------------------------------------------------------------------
+int fgl_plane_info(fgl_ctx* c, int plane, int* w, int* h, int* ch, int* bpc)
+{
+    ENTER(c);
+    if (plane < 0 || plane >= FGL_PLANE_COUNT || !w || !h || !ch || !bpc) return fgl_fail(c, FGL_ERR_INVALID, "fgl_plane_info: bad arguments");
+    if (plane <= FGL_PLANE_AO) *w = c->planes[plane].w, *h = c->planes[plane].h, *ch = is1ch(plane) ? 1 : 3, *bpc = 4;
+    else if (plane == FGL_PLANE_FRAME_RGB8) *w = c->planes[FGL_PLANE_FRAME].w, *h = c->planes[FGL_PLANE_FRAME].h, *ch = 3, *bpc = 1;
+    else if (plane == FGL_PLANE_SSAA_RGB8) *w = c->ssaaW, *h = c->ssaaH, *ch = 3, *bpc = 1;
+    else if (plane == FGL_PLANE_PRIMID_CAMERA) *w = c->visCamW, *h = c->visCamH, *ch = 1, *bpc = 4;
+    else *w = c->visLightW, *h = c->visLightH, *ch = 1, *bpc = 4;
+    return FGL_OK;
+}
+
+// device pointer + byte size of a plane in the reference's layout (AoS); 3-channel fp32 planes go through scanTmp
+static int plane_as_aos(fgl_ctx* c, int plane, const void** src, size_t* bytes)
+{
+    if (plane <= FGL_PLANE_AO)
+    {
+        PlaneH& p = c->planes[plane];
+        size_t  n = (size_t)p.w * p.h;
+        *bytes = n * p.ch * 4;
+        if (!p.buf.p) { *src = nullptr; *bytes = 0; return FGL_OK; }
+        if (int rc = materialize(c, plane)) return rc;
+        if (p.ch == 1) { *src = p.buf.p; return FGL_OK; }
+        if (int rc = fgl_reserve(c, c->scanTmp, *bytes)) return rc;
+        if (int rc = fgl_run_aos(c, (const float*)p.buf.p, (float*)c->scanTmp.p, n, p.ch, true)) return rc;
+        *src = c->scanTmp.p;
+        return FGL_OK;
+    }
+    if (plane == FGL_PLANE_FRAME_RGB8)
+    {
+        if (int rc = ensure_rgb8(c)) return rc;
+        *src = c->frameRgb8.p, *bytes = (size_t)c->planes[FGL_PLANE_FRAME].w * c->planes[FGL_PLANE_FRAME].h * 3;
+        return FGL_OK;
+    }
+    if (plane == FGL_PLANE_SSAA_RGB8)
+    {
+        *src = c->ssaaRgb8.p, *bytes = (size_t)c->ssaaW * c->ssaaH * 3;
+        return FGL_OK;
+    }
+    bool    cam = plane == FGL_PLANE_PRIMID_CAMERA;
+    DevBuf& vis = cam ? c->visCamera : c->visLight;
+    size_t  n = (size_t)(cam ? c->visCamW : c->visLightW) * (cam ? c->visCamH : c->visLightH);
+    *bytes = n * 4;
+    if (!n) { *src = nullptr; return FGL_OK; }
+    if (int rc = fgl_reserve(c, c->scanTmp, n * 4)) return rc;
+    if (int rc = fgl_run_ids(c, (const unsigned long long*)vis.p, n, (int*)c->scanTmp.p)) return rc;
+    *src = c->scanTmp.p;
+    return FGL_OK;
+}
+
+int fgl_read_plane(fgl_ctx* c, int plane, void* dst, size_t bytes)
+{
+    ENTER(c);
+    if (plane < 0 || plane >= FGL_PLANE_COUNT || !dst) return fgl_fail(c, FGL_ERR_INVALID, "fgl_read_plane: bad arguments");
+    if (int rc = flush(c)) return rc;
+    const void* src = nullptr;
+    size_t      n = 0;
+    if (int rc = plane_as_aos(c, plane, &src, &n)) return rc;
+    if (bytes != n) return fgl_fail(c, FGL_ERR_INVALID, "fgl_read_plane: size mismatch (have " + std::to_string(n) + ")");
+    if (n) FGL_CUDA(c, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+
+int fgl_write_plane(fgl_ctx* c, int plane, const void* src, size_t bytes)
+{
+    ENTER(c);
+    if (plane < 0 || plane > FGL_PLANE_AO || !src) return fgl_fail(c, FGL_ERR_INVALID, "fgl_write_plane: bad arguments");
+    if (int rc = flush(c)) return rc;
+    PlaneH& p = c->planes[plane];
+    size_t  n = (size_t)p.w * p.h;
+    if (!p.buf.p || bytes != n * p.ch * 4) return fgl_fail(c, FGL_ERR_INVALID, "fgl_write_plane: size mismatch");
+    p.fillPending = false;
+    if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = false;
+    if (p.ch == 1) FGL_CUDA(c, cudaMemcpyAsync(p.buf.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    else
+    {
+        if (int rc = fgl_reserve(c, c->scanTmp, bytes)) return rc;
+        FGL_CUDA(c, cudaMemcpyAsync(c->scanTmp.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (int rc = fgl_run_aos(c, (const float*)c->scanTmp.p, (float*)p.buf.p, n, p.ch, false)) return rc;
+    }
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+
+int fgl_copy_plane_rows_to_device(fgl_ctx* c, int plane, int row0, int row1, void* dst, size_t bytes)
+{
+    ENTER(c);
+    if (plane < 0 || plane >= FGL_PLANE_COUNT || !dst || row0 < 0 || row1 < row0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_copy_plane_rows_to_device: bad arguments");
+    if (int rc = flush(c)) return rc;
+    int w, h, ch, bpc;
+    fgl_plane_info(c, plane, &w, &h, &ch, &bpc);
+    if (row1 > h) return fgl_fail(c, FGL_ERR_INVALID, "fgl_copy_plane_rows_to_device: rows out of range");
+    size_t rowBytes = (size_t)w * ch * bpc, want = rowBytes * (row1 - row0);
+    if (bytes != want) return fgl_fail(c, FGL_ERR_INVALID, "fgl_copy_plane_rows_to_device: size mismatch (need " + std::to_string(want) + ")");
+    const void* src = nullptr;
+    size_t      n = 0;
+    if (plane == FGL_PLANE_FRAME_RGB8 && c->bandRgb8Valid && !c->frameRgb8Valid)
+    {   // sort-first: this GPU lit only its band; its rows are current
+        int b0, b1;
+        band_of(c, h, b0, b1);
+        if (row0 < b0 || row1 > b1) return fgl_fail(c, FGL_ERR_STATE, "rows outside the band this context rendered");
+        src = c->frameRgb8.p;
+    }
+    else if (int rc = plane_as_aos(c, plane, &src, &n)) return rc;
+    if (want) FGL_CUDA(c, cudaMemcpyAsync(dst, (const uint8_t*)src + rowBytes * row0, want, cudaMemcpyDeviceToDevice, c->stream));
+    return FGL_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------------------------------
+int fgl_enable_timing(fgl_ctx* c, int on) { ENTER(c); c->timing = on != 0; return FGL_OK; }
+int fgl_reset_timings(fgl_ctx* c)
+{
+    ENTER(c);
+    cudaStreamSynchronize(c->stream);
+    for (auto& t : c->timings) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+    c->timings.clear();
+    return FGL_OK;
+}
+int fgl_get_timings(fgl_ctx* c, FglTiming* out, int max, int* count)
+{
+    ENTER(c);
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<std::string> order;
+    std::map<std::string, FglTiming> agg;
+    for (auto& t : c->timings)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        auto it = agg.find(t.name);
+        if (it == agg.end())
+        {
+            FglTiming f;
+            memset(&f, 0, sizeof f);
+            strncpy(f.name, t.name.c_str(), sizeof f.name - 1);
+            it = agg.emplace(t.name, f).first;
+            order.push_back(t.name);
+        }
+        it->second.ms_total += ms, it->second.launches += 1, it->second.algorithmic_bytes += t.bytes;
+    }
+    int n = 0;
+    for (auto& name : order)
+        if (out && n < max) out[n++] = agg[name];
+    if (count) *count = n;
+    return FGL_OK;
+}
+int fgl_launch_count(fgl_ctx* c, uint64_t* o) { ENTER(c); if (o) *o = c->launches; return FGL_OK; }
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// fgl_internal.h — context layout and kernel entry points shared by the translation units of libforkergl_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "device_math.cuh"
+
+// ---- device-side records -----------------------------------------------------------------------------------
+// One draw call (= one Mesh::Draw of the reference, mesh.cpp:10-25) as the kernels see it.
+struct DrawCmdD
+{
+    const float *pos, *uv, *nrm, *tan;
+    const int *  pi, *ti, *ni;
+    FglMaterial  mat;
+    int          hasTangents, supportPBR, kind, firstPrim, nFaces;
+    float        model[16], view[16], proj[16], normal[9], lightSpace[16];
+    float        lm[16];  // DepthShader: uLightSpaceMatrix * uModelMatrix (depthshader.h:23-24)
+    float        lightPos[3], lightColor[3], eye[3];
+};
+
+// Per-triangle setup record, 48 bytes (three 16-byte words):
+//   w0 = X0 X1 X2 Y0 ; w1 = Y1 Y2 d0 d1 ; w2 = d2, bbox x (lo16 = xmin, hi16 = xmax), bbox y, flags
+struct TriSetup
+{
+    int4 w0, w1, w2;
+};
+enum { TRI_SKIP = 1, TRI_SMALL = 2, TRI_LARGE = 4 };
+
+// Per-triangle varyings of the camera-space programs (gshader.h:71-92), every attribute already times 1/w_clip.
+// 48 floats = 192 bytes: posWS[3], nrmWS[3], tanWS[3], lightNDC[3] as xyz triples, then u[3], v[3], oow[3], pad.
+struct TriVary
+{
+    float f[48];
+};
+
+struct RasterPass
+{
+    // target
+    int W, H, row0, row1;  // buffer size and the row band camera passes are restricted to
+    int passType, shadowOn;
+    float viewport[16];
+    // geometry
+    const DrawCmdD* draws;
+    int             nDraws, nPrims;
+    TriSetup*       setup;
+    TriVary*        vary;   // camera passes
+    float4*         zndc;   // shadow pass: DepthShader's vPositionNDC z row
+    int*            nblk;   // per triangle: number of 32x32 blocks of the large path (0 otherwise)
+    int*            blkScan;  // exclusive scan of nblk, nPrims + 1 entries
+    unsigned long long* vis;
+    const TexD*     textures;
+};
+
+struct PlanesD
+{
+    float* p[FGL_PLANE_AO + 1];  // SoA: channel c of pixel i at p[plane][c * N + i]
+};
+
+struct LightPass
+{
+    int     W, H, row0, row1;
+    PlanesD planes;
+    ShadowMapD sm;
+    int     shadowOn, shadowMode, useAO, writeF32;
+    float   eye[3], lightPos[3], lightColor[3];
+    float   biasSlope, biasMin, shadowIntensity, areaLight;
+    double  pcfFilter, pcssFilter;
+    uint8_t* rgb8;
+    const float2* disk;        // accepted unit-disk samples of the replayed stream (lighting phase)
+    const unsigned* chunkOf;   // PCSS: per pixel index of its first 32-sample chunk; NULL = PCF (2 * pixel)
+};
+
+// ---- host-side objects -----------------------------------------------------------------------------------
+struct DevBuf
+{
+    void*  p = nullptr;
+    size_t cap = 0;
+};
+
+struct PlaneH
+{
+    int    w = 0, h = 0, ch = 0;
+    DevBuf buf;
+    bool   fillPending = false;
+    float  fillValue = 0.f;
+    float  fillRGB[3] = { 0, 0, 0 };
+    bool   fillIsRGB = false;
+};
+
+struct TextureH
+{
+    DevBuf data;
+    TexD   desc;
+};
+struct VerticesH
+{
+    DevBuf pos, uv, nrm, tan;
+    int    nPos = 0, nUv = 0, nNrm = 0, nTan = 0;
+};
+struct MeshH
+{
+    int         vertices = -1, nFaces = 0;
+    DevBuf      pi, ti, ni;
+    FglMaterial mat;
+    int         hasTangents = 0, supportPBR = 0;
+};
+
+struct TimingRec
+{
+    std::string name;
+    cudaEvent_t e0, e1;
+    uint64_t    bytes;
+};
+
+struct fgl_ctx
+{
+    int          device = 0;
+    std::string  error;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    FglParams    params;
+    float        viewport[16], viewProj[16], lightSpace[16];
+    int          mode = FGL_MODE_FORWARD, pass = FGL_PASS_FORWARD, shadowOn = 1;
+    int          row0 = 0, row1 = -1;  // band; row1 < 0 = whole buffer
+
+    PlaneH planes[FGL_PLANE_AO + 1];
+    DevBuf frameRgb8, ssaaRgb8;
+    bool   frameRgb8Valid = false, bandRgb8Valid = false;
+    int    ssaaW = 0, ssaaH = 0;
+
+    // visibility buffers (depth|primitive id keys)
+    DevBuf visCamera, visLight;
+    int    visCamW = 0, visCamH = 0, visLightW = 0, visLightH = 0;
+    bool   visCamClear = false, visLightClear = false, depthInitPending = false;
+
+    // resources
+    std::vector<TextureH>  textures;
+    std::vector<VerticesH> vertices;
+    std::vector<MeshH>     meshes;
+    DevBuf                 texTable;
+    bool                   texTableDirty = true;
+
+    // pending draws of the current pass
+    std::vector<DrawCmdD> draws;
+    int                   primCounter = 0;  // submission index of the next triangle in this pass
+    int                   flushedPrims = 0;
+    DevBuf                drawsDev, setup, vary, zndc, nblk, blkScan, scanTmp;
+    void*                 pinned = nullptr;
+    size_t                pinnedCap = 0;
+
+    // sample stream (rng.cu)
+    struct SampleStream* stream_state = nullptr;
+
+    // instrumentation
+    bool                   timing = false;
+    std::vector<TimingRec> timings;
+    std::vector<cudaEvent_t> eventPool;
+    uint64_t               launches = 0;
+};
+
+// error helpers ------------------------------------------------------------------------------------------------
+int fgl_fail(fgl_ctx* c, int code, const std::string& msg);
+#define FGL_CUDA(c, call)                                                                                   \
+    do                                                                                                      \
+    {                                                                                                       \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return fgl_fail((c), FGL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+int  fgl_reserve(fgl_ctx* c, DevBuf& b, size_t bytes);  // grow-only device allocation
+void fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes);
+void fgl_time_end(fgl_ctx* c);
+
+// RAII bracket used around every kernel launch: counts the launch and, when enabled, records CUDA events.
+struct LaunchScope
+{
+    fgl_ctx* c;
+    LaunchScope(fgl_ctx* ctx, const char* name, uint64_t bytes) : c(ctx)
+    {
+        ++c->launches;
+        if (c->timing) fgl_time_begin(c, name, bytes);
+    }
+    ~LaunchScope()
+    {
+        if (c->timing) fgl_time_end(c);
+    }
+};
+
+// kernels (raster.cu) ------------------------------------------------------------------------------------------
+int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb8, const LightPass* forwardLight);
+// kernels (shade.cu)
+int fgl_run_fill(fgl_ctx* c, float* dst, size_t n, float value);
+int fgl_run_fill_rgb(fgl_ctx* c, float* dst, size_t nPixels, const float rgb[3]);
+int fgl_run_lighting(fgl_ctx* c, const LightPass& L);
+int fgl_run_quantize(fgl_ctx* c, const float* frame, size_t nPixels, uint8_t* rgb8);
+int fgl_run_ssaa(fgl_ctx* c, const uint8_t* rgb8, int W, int H, int k, uint8_t* out, int row0, int row1);
+int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind);
+int fgl_run_ids(fgl_ctx* c, const unsigned long long* vis, size_t n, int* out);
+int fgl_run_aos(fgl_ctx* c, const float* soa, float* aos, size_t nPixels, int channels, bool toAos);
+struct SsaoPass
+{
+    int          W, H, row0, row1;
+    const float *worldpos, *normal, *depth;
+    float*       ao;
+    float        viewProj[16], viewport[16];
+    float        radius, rangeCheckRadius, bias;
+    int          rangeCheck;
+    const float* ball;  // accepted unit-ball samples: x,y,z triples, 32 per pixel
+};
+int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S);

@@ -1,0 +1,523 @@
+// raster.cu — the raster passes (shadow / geometry / forward) of the frame as sm_100a kernels.
+//
+//   k_setup          one thread per triangle: the vertex program x3 (reference gshader.h:41-92 == phongshader.h:35-85
+//                    == pbrshader.h:35-85, depthshader.h:21-28), viewport + integer snap + clamped bounding box
+//                    (forkergl.cpp:241-255), classification for the two raster paths.
+//   k_raster_small   one thread per small triangle; k_raster_blocks: one warp per 32x32 block of a large triangle's
+//                    bounding box.  Coverage is the reference's double-precision barycentric test evaluated
+//                    literally (geometry.cpp:20-56), pre-filtered by exact integer edge functions; the depth test
+//                    (forkergl.cpp:180-200, strict-less, first submitted wins ties) is a 64-bit atomicMin on
+//                    (orderable(depth) << 32 | primitive id), which makes the result independent of scheduling.
+//   k_resolve_*      one thread per pixel: decode the winner, redo its barycentrics, run the fragment program
+//                    (depthshader.h:30-36, gshader.h:95-201, phongshader.h:90-169, pbrshader.h:90-180) and write the
+//                    SoA planes; pixels without a winner receive the planes' clear values (fused clear).
+#include <cub/device/device_scan.cuh>
+
+#include "fgl_internal.h"
+
+namespace
+{
+constexpr int kSmallArea = 32;  // clamped bbox area up to which a triangle takes the thread-per-triangle path
+constexpr int kBlk = 32;        // block edge of the warp path
+constexpr int kSaneCoord = 1 << 20;
+
+__device__ __forceinline__ const DrawCmdD& find_draw(const DrawCmdD* draws, int nDraws, int prim)
+{
+    int lo = 0, hi = nDraws - 1;
+    while (lo < hi)
+    {
+        int mid = (lo + hi + 1) >> 1;
+        if (draws[mid].firstPrim <= prim) lo = mid;
+        else hi = mid - 1;
+    }
+    return draws[lo];
+}
+
+__device__ __forceinline__ V3 ld3(const float* a, int i) { return v3(__ldg(a + 3 * (size_t)i), __ldg(a + 3 * (size_t)i + 1), __ldg(a + 3 * (size_t)i + 2)); }
+
+struct SetupRegs
+{
+    int   X[3], Y[3];
+    float d[3];
+    int   xmin, xmax, ymin, ymax, flags;
+};
+__device__ __forceinline__ SetupRegs load_setup(const TriSetup* s, int prim)
+{
+    const int4* p = reinterpret_cast<const int4*>(s + prim);
+    int4        a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    SetupRegs   r;
+    r.X[0] = a.x, r.X[1] = a.y, r.X[2] = a.z, r.Y[0] = a.w;
+    r.Y[1] = b.x, r.Y[2] = b.y, r.d[0] = __int_as_float(b.z), r.d[1] = __int_as_float(b.w);
+    r.d[2] = __int_as_float(c.x);
+    r.xmin = c.y & 0xffff, r.xmax = (c.y >> 16) & 0xffff;
+    r.ymin = c.z & 0xffff, r.ymax = (c.z >> 16) & 0xffff;
+    r.flags = c.w;
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin)
+{
+    int prim = primBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (prim >= P.nPrims) return;
+    const DrawCmdD& d = find_draw(P.draws, P.nDraws, prim);
+    int             face = prim - d.firstPrim;
+    bool            shadowPass = P.passType == FGL_PASS_SHADOW;
+
+    V4       ndc[3];
+    TriVary  vy;
+    float    zn[3] = { 0.f, 0.f, 0.f };
+    if (!shadowPass)
+    {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) vy.f[i] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        int pidx = __ldg(d.pi + face * 3 + k);
+        V3  p = ld3(d.pos, pidx);
+        V4  p4;
+        p4.x = p.x, p4.y = p.y, p4.z = p.z, p4.w = 1.f;
+        if (d.kind == FGL_SHADER_DEPTH)
+        {
+            V4 cs = mat4mul(d.lm, p4);
+            ndc[k] = vdivs4(cs, cs.w);
+            zn[k] = ndc[k].z;
+            continue;
+        }
+        V4    ws = mat4mul(d.model, p4);
+        V4    vs = mat4mul(d.view, ws);
+        V4    cs = mat4mul(d.proj, vs);
+        int   tidx = __ldg(d.ti + face * 3 + k);
+        float tu = __ldg(d.uv + 2 * (size_t)tidx), tv = __ldg(d.uv + 2 * (size_t)tidx + 1);
+        V3    nWS = mat3mul(d.normal, vnormalize(ld3(d.nrm, __ldg(d.ni + face * 3 + k))));  // mesh.cpp:46-50
+        float oow = 1.f / cs.w;
+        vy.f[42 + k] = oow;
+        vy.f[0 + 3 * k] = ws.x * oow, vy.f[1 + 3 * k] = ws.y * oow, vy.f[2 + 3 * k] = ws.z * oow;
+        vy.f[36 + k] = tu * oow, vy.f[39 + k] = tv * oow;
+        vy.f[9 + 3 * k] = nWS.x * oow, vy.f[10 + 3 * k] = nWS.y * oow, vy.f[11 + 3 * k] = nWS.z * oow;
+        if (d.hasTangents)
+        {
+            V3 tWS = mat3mul(d.normal, vnormalize(ld3(d.tan, pidx)));
+            vy.f[18 + 3 * k] = tWS.x * oow, vy.f[19 + 3 * k] = tWS.y * oow, vy.f[20 + 3 * k] = tWS.z * oow;
+        }
+        if (P.shadowOn)
+        {
+            V4 ls = mat4mul(d.lightSpace, ws);
+            ls = vdivs4(ls, ls.w);
+            vy.f[27 + 3 * k] = ls.x * oow, vy.f[28 + 3 * k] = ls.y * oow, vy.f[29 + 3 * k] = ls.z * oow;
+        }
+        ndc[k] = vdivs4(cs, cs.w);
+    }
+
+    // forkergl.cpp:241-255: viewport, integer snap, clamped bounding box
+    int   X[3], Y[3];
+    float dz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        V4 s = mat4mul(P.viewport, ndc[k]);
+        X[k] = f2i_x86(s.x), Y[k] = f2i_x86(s.y);
+        dz[k] = s.z;
+    }
+    int mnx = min(X[0], min(X[1], X[2])), mxx = max(X[0], max(X[1], X[2]));
+    int mny = min(Y[0], min(Y[1], Y[2])), mxy = max(Y[0], max(Y[1], Y[2]));
+    int xmin = clampi(mnx, 0, P.W - 1), xmax = clampi(mxx, 0, P.W - 1);
+    int ymin = clampi(mny, 0, P.H - 1), ymax = clampi(mxy, 0, P.H - 1);
+
+    TriCover tc = make_cover(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
+    int      flags = 0;
+    bool     sane = max(max(abs(mnx), abs(mxx)), max(abs(mny), abs(mxy))) <= kSaneCoord && mnx != (int)0x80000000 && mny != (int)0x80000000;
+    if (!tc.valid) flags = TRI_SKIP;
+    // a triangle whose own bounding box misses the buffer only scans pixels outside itself (all rejected)
+    if (sane && (mxx < 0 || mnx > P.W - 1 || mxy < 0 || mny > P.H - 1)) flags = TRI_SKIP;
+    if (!shadowPass)
+    {   // sort-first row band of this GPU
+        ymin = max(ymin, P.row0), ymax = min(ymax, P.row1 - 1);
+        if (ymin > ymax) flags = TRI_SKIP, ymin = ymax = 0;
+    }
+    int bw = xmax - xmin + 1, bh = ymax - ymin + 1, nb = 0;
+    if (!(flags & TRI_SKIP))
+    {
+        if (bw * bh <= kSmallArea) flags |= TRI_SMALL;
+        else
+        {
+            flags |= TRI_LARGE;
+            nb = ((bw + kBlk - 1) / kBlk) * ((bh + kBlk - 1) / kBlk);
+        }
+        if (sane) flags |= 8;
+    }
+    P.nblk[prim] = nb;
+
+    int4* so = reinterpret_cast<int4*>(P.setup + prim);
+    so[0] = make_int4(X[0], X[1], X[2], Y[0]);
+    so[1] = make_int4(Y[1], Y[2], __float_as_int(dz[0]), __float_as_int(dz[1]));
+    so[2] = make_int4(__float_as_int(dz[2]), xmin | (xmax << 16), ymin | (ymax << 16), flags);
+    if (shadowPass) P.zndc[prim] = make_float4(zn[0], zn[1], zn[2], 0.f);
+    else if (!(flags & TRI_SKIP))
+    {
+        float4* vo = reinterpret_cast<float4*>(P.vary + prim);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) vo[i] = make_float4(vy.f[4 * i], vy.f[4 * i + 1], vy.f[4 * i + 2], vy.f[4 * i + 3]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Exact integer edge functions (valid while |coords| <= 2^20): a pixel can pass the reference's test only if
+// all three are >= 0 after multiplying by the sign of the signed area (DESIGN.md "coverage pre-filter").
+struct EdgeInt
+{
+    long long e0, e1, e2;        // values at the current pixel
+    long long dx0, dx1, dx2;     // increments for px + 1
+    long long dy0, dy1, dy2;     // increments for py + 1
+};
+__device__ __forceinline__ EdgeInt make_edges(const SetupRegs& s, int px, int py)
+{
+    long long ax = s.X[0], ay = s.Y[0], bx = s.X[1], by = s.Y[1], cx = s.X[2], cy = s.Y[2];
+    long long rz = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay);
+    long long sg = rz < 0 ? -1 : 1;
+    long long rx = (cx - ax) * (ay - py) - (ax - px) * (cy - ay);
+    long long ry = (ax - px) * (by - ay) - (bx - ax) * (ay - py);
+    EdgeInt   e;
+    e.e1 = sg * rx, e.e2 = sg * ry, e.e0 = sg * (rz - rx - ry);
+    e.dx1 = sg * (cy - ay), e.dy1 = -sg * (cx - ax);
+    e.dx2 = -sg * (by - ay), e.dy2 = sg * (bx - ax);
+    e.dx0 = -(e.dx1 + e.dx2), e.dy0 = -(e.dy1 + e.dy2);
+    return e;
+}
+
+__device__ __forceinline__ void depth_test_pixel(const RasterPass& P, const TriCover& tc, const SetupRegs& s, int prim, int px, int py)
+{
+    V3 bary;
+    if (!cover_test(tc, px, py, bary)) return;
+    float z = vdot(bary, v3(s.d[0], s.d[1], s.d[2]));  // forkergl.cpp:180
+    if (!(z < 3.402823466e+38f)) return;                // never below the FLT_MAX clear value (forkergl.cpp:189)
+    unsigned long long  key = ((unsigned long long)depth_to_ordered(z) << 32) | (unsigned)prim;
+    unsigned long long* cell = P.vis + (size_t)px + (size_t)py * P.W;
+    if (key < *((volatile unsigned long long*)cell)) atomicMin(cell, key);
+}
+
+__global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegin)
+{
+    int prim = primBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (prim >= P.nPrims) return;
+    int flags = __ldg(&reinterpret_cast<const int4*>(P.setup + prim)[2].w);
+    if (!(flags & TRI_SMALL)) return;
+    SetupRegs s = load_setup(P.setup, prim);
+    TriCover  tc = make_cover(s.X[0], s.Y[0], s.X[1], s.Y[1], s.X[2], s.Y[2]);
+    bool      sane = flags & 8;
+    EdgeInt   e = make_edges(s, s.xmin, s.ymin);
+    for (int px = s.xmin; px <= s.xmax; ++px)
+    {
+        long long c0 = e.e0, c1 = e.e1, c2 = e.e2;
+        for (int py = s.ymin; py <= s.ymax; ++py)
+        {
+            if (!sane || (c0 | c1 | c2) >= 0) depth_test_pixel(P, tc, s, prim, px, py);
+            c0 += e.dy0, c1 += e.dy1, c2 += e.dy2;
+        }
+        e.e0 += e.dx0, e.e1 += e.dx1, e.e2 += e.dx2;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBegin, int nNew)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    const int total = P.blkScan[nNew];  // blkScan = exclusive scan over the nNew triangles of this flush (+ total)
+    int       cachedTri = -1, cachedBegin = 0, cachedEnd = 0;
+    SetupRegs s;
+    TriCover  tc;
+    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warpsPerGrid)
+    {
+        if (item < cachedBegin || item >= cachedEnd)
+        {   // upper_bound over the exclusive scan: last triangle whose first block index is <= item
+            int lo = 0, hi = nNew - 1;
+            while (lo < hi)
+            {
+                int mid = (lo + hi + 1) >> 1;
+                if (__ldg(P.blkScan + mid) <= item) lo = mid;
+                else hi = mid - 1;
+            }
+            cachedTri = primBegin + lo;
+            cachedBegin = __ldg(P.blkScan + lo), cachedEnd = __ldg(P.blkScan + lo + 1);
+            s = load_setup(P.setup, cachedTri);
+            tc = make_cover(s.X[0], s.Y[0], s.X[1], s.Y[1], s.X[2], s.Y[2]);
+        }
+        int local = item - cachedBegin;
+        int nbx = (s.xmax - s.xmin + kBlk) / kBlk;
+        int bx = local % nbx, by = local / nbx;
+        int px = s.xmin + bx * kBlk + lane;
+        int y0 = s.ymin + by * kBlk, y1 = min(y0 + kBlk - 1, s.ymax);
+        if (px > s.xmax) continue;
+        bool    sane = s.flags & 8;
+        EdgeInt e = make_edges(s, px, y0);
+        for (int py = y0; py <= y1; ++py)
+        {
+            if (!sane || (e.e0 | e.e1 | e.e2) >= 0) depth_test_pixel(P, tc, s, cachedTri, px, py);
+            e.e0 += e.dy0, e.e1 += e.dy1, e.e2 += e.dy2;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool decode_winner(const RasterPass& P, size_t idx, int px, int py, int& prim, V3& bary, float& depth)
+{
+    unsigned long long key = P.vis[idx];
+    if (key == FGL_VIS_EMPTY) return false;
+    prim = (int)(unsigned)(key & 0xffffffffull);
+    SetupRegs s = load_setup(P.setup, prim);
+    TriCover  tc = make_cover(s.X[0], s.Y[0], s.X[1], s.Y[1], s.X[2], s.Y[2]);
+    cover_test(tc, px, py, bary);
+    depth = vdot(bary, v3(s.d[0], s.d[1], s.d[2]));
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_shadow(RasterPass P, float* shadowPlane, float* depthPlane)
+{
+    size_t n = (size_t)P.W * P.H;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int   px = (int)(idx % P.W), py = (int)(idx / P.W);
+    int   prim;
+    V3    bary;
+    float depth, sh = 0.f;
+    if (decode_winner(P, idx, px, py, prim, bary, depth))
+    {
+        float4 z = __ldg(P.zndc + prim);
+        sh = interp(z.x, z.y, z.z, bary) * 0.5f + 0.5f;  // depthshader.h:30-36
+    }
+    else depth = 3.402823466e+38f;
+    shadowPlane[idx] = sh;
+    depthPlane[idx] = depth;
+}
+
+struct Surface
+{
+    V3    posWS, normal, lightNDC;
+    float u, v;
+};
+
+// common head of the camera-space fragment programs: gshader.h:95-146 == phongshader.h:90-128 == pbrshader.h:90-128
+__device__ __forceinline__ Surface interpolate_surface(const RasterPass& P, const DrawCmdD& d, const float* vy, V3 bary, int normalMapId)
+{
+    Surface s;
+    V3      pos = v3(interp(vy[0], vy[3], vy[6], bary), interp(vy[1], vy[4], vy[7], bary), interp(vy[2], vy[5], vy[8], bary));
+    float   tu = interp(vy[36], vy[37], vy[38], bary), tv = interp(vy[39], vy[40], vy[41], bary);
+    V3      nrm = v3(interp(vy[9], vy[12], vy[15], bary), interp(vy[10], vy[13], vy[16], bary), interp(vy[11], vy[14], vy[17], bary));
+    float   w = 1.f / vdot(v3(vy[42], vy[43], vy[44]), bary);
+    pos = vscale(pos, w);
+    tu *= w, tv *= w;
+    nrm = vscale(nrm, w);
+    V3 N = vnormalize(nrm);
+    V3 normal = N;
+    if (d.hasTangents && normalMapId >= 0)
+    {
+        V3 tg = v3(interp(vy[18], vy[21], vy[24], bary), interp(vy[19], vy[22], vy[25], bary), interp(vy[20], vy[23], vy[26], bary));
+        tg = vscale(tg, w);
+        V3 T = vnormalize(vadd(tg, v3(0.001f, 0.001f, 0.001f)));
+        T = vnormalize(vsub(T, vscale(N, vdot(T, N))));
+        V3 B = vnormalize(vcross(N, T));
+        V3 sn = tex_sample(P.textures[normalMapId], tu, tv);
+        sn = vnormalize(vsub(vscale(sn, 2.f), v3(1.f, 1.f, 1.f)));
+        normal = vnormalize(v3(vdot(v3(T.x, B.x, N.x), sn), vdot(v3(T.y, B.y, N.y), sn), vdot(v3(T.z, B.z, N.z), sn)));
+    }
+    s.posWS = pos, s.normal = normal, s.u = tu, s.v = tv;
+    s.lightNDC = v3(0.f, 0.f, 0.f);
+    if (P.shadowOn)
+    {
+        V3 l = v3(interp(vy[27], vy[30], vy[33], bary), interp(vy[28], vy[31], vy[34], bary), interp(vy[29], vy[32], vy[35], bary));
+        s.lightNDC = vscale(l, w);
+    }
+    return s;
+}
+
+__device__ __forceinline__ void st3(float* plane, size_t n, size_t idx, V3 v)
+{
+    plane[idx] = v.x, plane[n + idx] = v.y, plane[2 * n + idx] = v.z;
+}
+
+__device__ __forceinline__ void load_vary(const TriVary* vary, int prim, float* vy)
+{
+    const float4* p = reinterpret_cast<const float4*>(vary + prim);
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+    {
+        float4 q = __ldg(p + i);
+        vy[4 * i] = q.x, vy[4 * i + 1] = q.y, vy[4 * i + 2] = q.z, vy[4 * i + 3] = q.w;
+    }
+}
+
+// gshader.h:95-201 + the G-buffer writes of forkergl.cpp:211-223
+__global__ void __launch_bounds__(128) k_resolve_geometry(RasterPass P, PlanesD out)
+{
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = P.row0 + blockIdx.y;
+    if (px >= P.W || py >= P.row1) return;
+    size_t n = (size_t)P.W * P.H, idx = (size_t)px + (size_t)py * P.W;
+    int    prim;
+    V3     bary;
+    float  depth;
+    V3     z3 = v3(0.f, 0.f, 0.f);
+    if (!decode_winner(P, idx, px, py, prim, bary, depth))
+    {
+        out.p[FGL_PLANE_DEPTH][idx] = 3.402823466e+38f;
+        st3(out.p[FGL_PLANE_NORMAL], n, idx, z3);
+        st3(out.p[FGL_PLANE_WORLDPOS], n, idx, z3);
+        if (P.shadowOn) st3(out.p[FGL_PLANE_LIGHTNDC], n, idx, z3);
+        st3(out.p[FGL_PLANE_ALBEDO], n, idx, z3);
+        st3(out.p[FGL_PLANE_EMISSIVE], n, idx, z3);
+        st3(out.p[FGL_PLANE_PARAM], n, idx, z3);
+        out.p[FGL_PLANE_SHADINGTYPE][idx] = 0.f;
+        out.p[FGL_PLANE_AO][idx] = 1.f;
+        return;
+    }
+    const DrawCmdD&    d = find_draw(P.draws, P.nDraws, prim);
+    const FglMaterial& m = d.mat;
+    float              vy[48];
+    load_vary(P.vary, prim, vy);
+    Surface s = interpolate_surface(P, d, vy, bary, m.normal_map);
+    V3      albedo, emissive, param;
+    float   type;
+    if (d.supportPBR)
+    {
+        albedo = m.base_color_map >= 0 ? tex_sample(P.textures[m.base_color_map], s.u, s.v) : v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+        emissive = m.pbr_emissive_map >= 0 ? tex_sample(P.textures[m.pbr_emissive_map], s.u, s.v) : v3(m.ke[0], m.ke[1], m.ke[2]);
+        float roughness = m.roughness_map >= 0 ? tex_sample_float(P.textures[m.roughness_map], s.u, s.v) : m.roughness;
+        float metalness = m.metalness_map >= 0 ? tex_sample_float(P.textures[m.metalness_map], s.u, s.v) : m.metalness;
+        float ao = m.ao_map >= 0 ? tex_sample_float(P.textures[m.ao_map], s.u, s.v) : 1.f;
+        param = v3(ao, metalness, roughness);
+        type = 1.f;
+    }
+    else
+    {
+        emissive = m.emissive_map >= 0 ? tex_sample(P.textures[m.emissive_map], s.u, s.v) : v3(m.ke[0], m.ke[1], m.ke[2]);
+        albedo = m.diffuse_map >= 0 ? tex_sample(P.textures[m.diffuse_map], s.u, s.v) : v3(m.kd[0], m.kd[1], m.kd[2]);
+        float shininess = m.specular_map >= 0 ? tex_sample_float(P.textures[m.specular_map], s.u, s.v) + 5 : 1.f;
+        param = v3(1.f, m.ks[0], shininess);
+        type = 0.f;
+    }
+    out.p[FGL_PLANE_DEPTH][idx] = depth;
+    st3(out.p[FGL_PLANE_NORMAL], n, idx, s.normal);
+    st3(out.p[FGL_PLANE_WORLDPOS], n, idx, s.posWS);
+    if (P.shadowOn) st3(out.p[FGL_PLANE_LIGHTNDC], n, idx, s.lightNDC);
+    st3(out.p[FGL_PLANE_ALBEDO], n, idx, albedo);
+    st3(out.p[FGL_PLANE_EMISSIVE], n, idx, emissive);
+    st3(out.p[FGL_PLANE_PARAM], n, idx, param);
+    out.p[FGL_PLANE_SHADINGTYPE][idx] = type;
+    out.p[FGL_PLANE_AO][idx] = 1.f;
+}
+
+// Forward mode (phongshader.h:90-169, pbrshader.h:90-180): only the depth-test winner's colour survives in the
+// reference's FrameBuffer, so the programs run once per covered pixel.  Hard shadows only need the shadow map; the
+// stochastic filters additionally need each winner's position in the sample stream (see stream.cu).
+__global__ void __launch_bounds__(128) k_resolve_forward(RasterPass P, PlanesD out, LightPass L)
+{
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = P.row0 + blockIdx.y;
+    if (px >= P.W || py >= P.row1) return;
+    size_t n = (size_t)P.W * P.H, idx = (size_t)px + (size_t)py * P.W;
+    int    prim;
+    V3     bary;
+    float  depth;
+    if (!decode_winner(P, idx, px, py, prim, bary, depth))
+    {
+        out.p[FGL_PLANE_DEPTH][idx] = 3.402823466e+38f;
+        return;  // FrameBuffer keeps its clear colour
+    }
+    out.p[FGL_PLANE_DEPTH][idx] = depth;
+    const DrawCmdD&    d = find_draw(P.draws, P.nDraws, prim);
+    const FglMaterial& m = d.mat;
+    float              vy[48];
+    load_vary(P.vary, prim, vy);
+    bool    pbr = d.kind == FGL_SHADER_PBR;
+    Surface s = interpolate_surface(P, d, vy, bary, pbr ? m.pbr_normal_map : m.normal_map);
+    V3      lp = v3(d.lightPos[0], d.lightPos[1], d.lightPos[2]), ep = v3(d.eye[0], d.eye[1], d.eye[2]);
+    V3      lightDir = vnormalize(vsub(lp, s.posWS)), viewDir = vnormalize(vsub(ep, s.posWS));
+    V3      halfwayDir = vnormalize(vadd(lightDir, viewDir));
+    float   visibility = 0.f;
+    if (P.shadowOn)
+    {   // shadow.cpp:109-132, HardShadow branch
+        V3    sc = vadd(vscale(s.lightNDC, 0.5f), v3(0.5f, 0.5f, 0.5f));
+        float bias = fmaxf(L.biasSlope * (1.f - vdot(s.normal, lightDir)), L.biasMin);
+        float sampled = shadow_lookup(L.sm, sc.x, sc.y);
+        visibility = (sc.z <= sampled + bias) ? 1.f : 0.f;
+    }
+    LightConsts lc;
+    lc.shadowIntensity = L.shadowIntensity, lc.shadowOn = P.shadowOn;
+    V3 lcol = v3(d.lightColor[0], d.lightColor[1], d.lightColor[2]);
+    V3 color;
+    if (pbr)
+    {
+        V3    albedo = m.base_color_map >= 0 ? tex_sample(P.textures[m.base_color_map], s.u, s.v) : v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+        V3    emissive = m.pbr_emissive_map >= 0 ? tex_sample(P.textures[m.pbr_emissive_map], s.u, s.v) : v3(m.pbr_ke[0], m.pbr_ke[1], m.pbr_ke[2]);
+        float roughness = m.roughness_map >= 0 ? tex_sample_float(P.textures[m.roughness_map], s.u, s.v) : m.roughness;
+        float metalness = m.metalness_map >= 0 ? tex_sample_float(P.textures[m.metalness_map], s.u, s.v) : m.metalness;
+        float ao = m.ao_map >= 0 ? tex_sample_float(P.textures[m.ao_map], s.u, s.v) : 1.f;
+        color = pbr_light(lc, lightDir, viewDir, halfwayDir, s.normal, visibility, albedo, emissive, v3(ao, metalness, roughness), lcol);
+    }
+    else
+    {
+        V3    diffuseColor = m.diffuse_map >= 0 ? tex_sample(P.textures[m.diffuse_map], s.u, s.v) : v3(m.kd[0], m.kd[1], m.kd[2]);
+        V3    emissive = m.emissive_map >= 0 ? tex_sample(P.textures[m.emissive_map], s.u, s.v) : v3(m.ke[0], m.ke[1], m.ke[2]);
+        float shininess = 1.f;
+        if (m.specular_map >= 0) shininess = tex_sample_float(P.textures[m.specular_map], s.u, s.v) + 5;
+        color = blinn_phong_light(lc, lightDir, halfwayDir, s.normal, visibility, diffuseColor, emissive, v3(m.ka[0], m.ks[0], shininess), lcol);
+    }
+    st3(out.p[FGL_PLANE_FRAME], n, idx, color);
+}
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------------------
+int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb8, const LightPass* forwardLight)
+{
+    (void)rgb8;
+    cudaStream_t st = c->stream;
+    int          primBegin = c->flushedPrims;
+    int          nNew = P.nPrims - primBegin;
+    size_t       nPix = (size_t)P.W * P.H;
+    if (nNew > 0)
+    {
+        {
+            LaunchScope ls(c, "setup", (uint64_t)nNew * 320);
+            k_setup<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin);
+        }
+        // exclusive scan of the block counts of the new triangles -> blkScan[primBegin .. nPrims]
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
+        if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
+        {
+            LaunchScope ls(c, "scan", (uint64_t)nNew * 8);
+            // the scan runs over nNew + 1 inputs so that entry nNew holds the total (nblk has one spare, zeroed, slot)
+            cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
+        }
+        {
+            LaunchScope ls(c, "raster_small", 0);
+            k_raster_small<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin);
+        }
+        {
+            LaunchScope ls(c, "raster_blocks", 0);
+            k_raster_blocks<<<148 * 8, 256, 0, st>>>(P, primBegin, nNew);
+        }
+    }
+    if (P.passType == FGL_PASS_SHADOW)
+    {
+        LaunchScope ls(c, "resolve_shadow", (uint64_t)nPix * 16);
+        k_resolve_shadow<<<(unsigned)((nPix + 255) / 256), 256, 0, st>>>(P, planes.p[FGL_PLANE_SHADOW], planes.p[FGL_PLANE_DEPTH]);
+    }
+    else
+    {
+        dim3 grid((P.W + 127) / 128, P.row1 - P.row0);
+        if (P.passType == FGL_PASS_GEOMETRY)
+        {
+            LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88);
+            k_resolve_geometry<<<grid, 128, 0, st>>>(P, planes);
+        }
+        else if (P.passType == FGL_PASS_FORWARD)
+        {
+            LaunchScope ls(c, "resolve_forward", (uint64_t)P.W * (P.row1 - P.row0) * 24);
+            k_resolve_forward<<<grid, 128, 0, st>>>(P, planes, *forwardLight);
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("raster launch: ") + cudaGetErrorString(e));
+    return FGL_OK;
+}

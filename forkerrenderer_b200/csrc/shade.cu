@@ -1,0 +1,493 @@
+// shade.cu — the screen-space passes: deferred lighting (forkergl.cpp:326-380) fused with the shadow filters
+// (shadow.cpp:23-132) and the 8-bit quantise (buffer.cpp:113-126); SSAO (render.cpp:214-286); the in-place
+// Gaussian blur as the recurrence it is (buffer.cpp:59-98); the SSAA box resolve (render.cpp:291-343); clears and
+// layout conversions for the host accessors.
+#include "fgl_internal.h"
+
+namespace
+{
+__device__ __forceinline__ V3 ld3s(const float* plane, size_t n, size_t idx) { return v3(plane[idx], plane[n + idx], plane[2 * n + idx]); }
+
+__device__ __forceinline__ uint8_t quant8(float v) { return (uint8_t)f2i_x86(v * 254.99f); }  // buffer.cpp:121-122
+
+// ---- clears ------------------------------------------------------------------------------------------------------
+__global__ void k_fill(float* dst, size_t n, float value)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = value;
+}
+
+// ---- lighting, one thread per pixel (HardShadow or shadows off) ----------------------------------------------------
+struct PixelIn
+{
+    V3    pos, nrm, lndc, albedo, emissive, param;
+    float type;
+};
+
+__device__ __forceinline__ V3 shade_pixel(const LightPass& L, const PixelIn& in, float visibility, V3 lightDir, V3 viewDir)
+{
+    LightConsts lc;
+    lc.shadowIntensity = L.shadowIntensity, lc.shadowOn = L.shadowOn;
+    V3 rad = v3(L.lightColor[0], L.lightColor[1], L.lightColor[2]);
+    if (in.type < 0.5f)  // deferred Blinn-Phong receives viewDir where the halfway vector is expected (forkergl.cpp:369)
+        return blinn_phong_light(lc, lightDir, viewDir, in.nrm, visibility, in.albedo, in.emissive, in.param, rad);
+    return pbr_light(lc, lightDir, viewDir, vnormalize(vadd(lightDir, viewDir)), in.nrm, visibility, in.albedo, in.emissive, in.param, rad);
+}
+
+__device__ __forceinline__ PixelIn load_pixel(const LightPass& L, size_t n, size_t idx)
+{
+    PixelIn in;
+    in.pos = ld3s(L.planes.p[FGL_PLANE_WORLDPOS], n, idx);
+    in.nrm = ld3s(L.planes.p[FGL_PLANE_NORMAL], n, idx);
+    in.lndc = L.shadowOn ? ld3s(L.planes.p[FGL_PLANE_LIGHTNDC], n, idx) : v3(0.f, 0.f, 0.f);
+    in.albedo = ld3s(L.planes.p[FGL_PLANE_ALBEDO], n, idx);
+    in.emissive = ld3s(L.planes.p[FGL_PLANE_EMISSIVE], n, idx);
+    in.param = ld3s(L.planes.p[FGL_PLANE_PARAM], n, idx);
+    in.type = L.planes.p[FGL_PLANE_SHADINGTYPE][idx];
+    in.param.x *= L.planes.p[FGL_PLANE_AO][idx];  // forkergl.cpp:350
+    return in;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
+{
+    const size_t n = (size_t)L.W * L.H;
+    const size_t begin = (size_t)L.row0 * L.W, end = (size_t)L.row1 * L.W;
+    size_t       base = begin + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (base >= end) return;
+    V3 eye = v3(L.eye[0], L.eye[1], L.eye[2]), lp = v3(L.lightPos[0], L.lightPos[1], L.lightPos[2]);
+
+    float in[19][VEC];
+    {
+        const float* src[19];
+        int          k = 0;
+        for (int c = 0; c < 3; ++c) src[k++] = L.planes.p[FGL_PLANE_WORLDPOS] + c * n;
+        for (int c = 0; c < 3; ++c) src[k++] = L.planes.p[FGL_PLANE_NORMAL] + c * n;
+        for (int c = 0; c < 3; ++c) src[k++] = L.shadowOn ? L.planes.p[FGL_PLANE_LIGHTNDC] + c * n : nullptr;
+        for (int c = 0; c < 3; ++c) src[k++] = L.planes.p[FGL_PLANE_ALBEDO] + c * n;
+        for (int c = 0; c < 3; ++c) src[k++] = L.planes.p[FGL_PLANE_EMISSIVE] + c * n;
+        for (int c = 0; c < 3; ++c) src[k++] = L.planes.p[FGL_PLANE_PARAM] + c * n;
+        src[k++] = L.planes.p[FGL_PLANE_SHADINGTYPE];
+#pragma unroll
+        for (int j = 0; j < 19; ++j)
+        {
+            if (src[j] == nullptr)
+            {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) in[j][v] = 0.f;
+            }
+            else if constexpr (VEC == 4)
+            {
+                float4 q = __ldcs(reinterpret_cast<const float4*>(src[j] + base));
+                in[j][0] = q.x, in[j][1] = q.y, in[j][2] = q.z, in[j][3] = q.w;
+            }
+            else in[j][0] = __ldcs(src[j] + base);
+        }
+    }
+    float ao[VEC];
+    if constexpr (VEC == 4)
+    {
+        float4 q = __ldcs(reinterpret_cast<const float4*>(L.planes.p[FGL_PLANE_AO] + base));
+        ao[0] = q.x, ao[1] = q.y, ao[2] = q.z, ao[3] = q.w;
+    }
+    else ao[0] = __ldcs(L.planes.p[FGL_PLANE_AO] + base);
+
+    float   outc[3][VEC];
+    uint8_t q8[3 * VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+    {
+        PixelIn p;
+        p.pos = v3(in[0][v], in[1][v], in[2][v]);
+        p.nrm = v3(in[3][v], in[4][v], in[5][v]);
+        p.lndc = v3(in[6][v], in[7][v], in[8][v]);
+        p.albedo = v3(in[9][v], in[10][v], in[11][v]);
+        p.emissive = v3(in[12][v], in[13][v], in[14][v]);
+        p.param = v3(in[15][v], in[16][v], in[17][v]);
+        p.type = in[18][v];
+        p.param.x *= ao[v];
+        V3    lightDir = vnormalize(vsub(lp, p.pos)), viewDir = vnormalize(vsub(eye, p.pos));
+        float visibility = 0.f;
+        if (L.shadowOn)
+        {   // shadow.cpp:109-132 with HardShadow (shadow.cpp:38-45)
+            V3    sc = vadd(vscale(p.lndc, 0.5f), v3(0.5f, 0.5f, 0.5f));
+            float bias = fmaxf(L.biasSlope * (1.f - vdot(p.nrm, lightDir)), L.biasMin);
+            float sampled = shadow_lookup(L.sm, sc.x, sc.y);
+            visibility = (sc.z <= sampled + bias) ? 1.f : 0.f;
+        }
+        V3 col = shade_pixel(L, p, visibility, lightDir, viewDir);
+        outc[0][v] = col.x, outc[1][v] = col.y, outc[2][v] = col.z;
+        q8[3 * v] = quant8(col.x), q8[3 * v + 1] = quant8(col.y), q8[3 * v + 2] = quant8(col.z);
+    }
+    if (L.writeF32)
+    {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+            float* dst = L.planes.p[FGL_PLANE_FRAME] + c * n + base;
+            if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(outc[c][0], outc[c][1], outc[c][2], outc[c][3]));
+            else *dst = outc[c][0];
+        }
+    }
+    if constexpr (VEC == 4)
+    {
+        uint32_t w[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            w[i] = (uint32_t)q8[4 * i] | ((uint32_t)q8[4 * i + 1] << 8) | ((uint32_t)q8[4 * i + 2] << 16) | ((uint32_t)q8[4 * i + 3] << 24);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(L.rgb8 + base * 3);
+        dst[0] = w[0], dst[1] = w[1], dst[2] = w[2];
+    }
+    else
+    {
+        L.rgb8[base * 3] = q8[0], L.rgb8[base * 3 + 1] = q8[1], L.rgb8[base * 3 + 2] = q8[2];
+    }
+}
+
+// ---- lighting, one warp per pixel (PCF / PCSS): lane = tap of the replayed sample stream ---------------------------
+// shadow.cpp:47-63.  `first` = index of the first of the 64 accepted disk samples this filter consumes.
+__device__ __forceinline__ float pcf_warp(const LightPass& L, V3 sc, float bias, float filterSize, size_t first, int lane)
+{
+    int cnt = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+        float2 d = __ldg(L.disk + first + h * 32 + lane);
+        float  u = sc.x + d.x * filterSize, v = sc.y + d.y * filterSize;
+        float  sampleDepth = shadow_lookup(L.sm, u, v);
+        cnt += __popc(__ballot_sync(0xffffffffu, sc.z <= sampleDepth + bias));
+    }
+    return (float)cnt * (1.f / 64.f);  // 64 additions of 1/64 are exact: the sum is count / 64
+}
+
+// shadow.cpp:65-90 over the 32 samples starting at `first`; returns dBlocker (0 when no tap blocks)
+__device__ __forceinline__ float blocker_warp(const LightPass& L, V3 sc, float bias, size_t first, int lane)
+{
+    float2   d = __ldg(L.disk + first + lane);
+    float    ox = (float)((double)d.x * L.pcssFilter), oy = (float)((double)d.y * L.pcssFilter);
+    float    sampleDepth = shadow_lookup(L.sm, sc.x + ox, sc.y + oy);
+    unsigned mask = __ballot_sync(0xffffffffu, sc.z > sampleDepth + bias);
+    if (mask == 0) return 0.f;
+    float sum = 0.f;
+    float n = 0.f;
+    for (unsigned m = mask; m; m &= m - 1)
+    {   // ordered sum over the blocking taps, in tap order
+        int b = __ffs(m) - 1;
+        sum += __shfl_sync(0xffffffffu, sampleDepth, b);
+        n += 1.f;
+    }
+    return sum / n;
+}
+
+__global__ void __launch_bounds__(256) k_lighting_warp(LightPass L)
+{
+    const size_t n = (size_t)L.W * L.H;
+    const int    lane = threadIdx.x & 31;
+    size_t       idx = (size_t)L.row0 * L.W + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (idx >= (size_t)L.row1 * L.W) return;
+    PixelIn p = load_pixel(L, n, idx);
+    V3      eye = v3(L.eye[0], L.eye[1], L.eye[2]), lp = v3(L.lightPos[0], L.lightPos[1], L.lightPos[2]);
+    V3      lightDir = vnormalize(vsub(lp, p.pos)), viewDir = vnormalize(vsub(eye, p.pos));
+    V3      sc = vadd(vscale(p.lndc, 0.5f), v3(0.5f, 0.5f, 0.5f));
+    float   bias = fmaxf(L.biasSlope * (1.f - vdot(p.nrm, lightDir)), L.biasMin);
+    float   visibility;
+    if (L.shadowMode == FGL_SHADOW_PCF) visibility = pcf_warp(L, sc, bias, (float)L.pcfFilter, idx * 64, lane);
+    else
+    {   // shadow.cpp:92-106
+        size_t first = (size_t)L.chunkOf[idx] * 32;
+        float  dBlocker = blocker_warp(L, sc, bias, first, lane);
+        if ((double)dBlocker < 0.001) visibility = 1.f;
+        else
+        {
+            float penumbra = (sc.z - dBlocker) * L.areaLight / dBlocker;
+            float filterSize = (float)(L.pcfFilter * (double)penumbra);
+            visibility = pcf_warp(L, sc, bias, filterSize, first + 32, lane);
+        }
+    }
+    if (lane != 0) return;
+    V3 col = shade_pixel(L, p, visibility, lightDir, viewDir);
+    if (L.writeF32)
+    {
+        float* f = L.planes.p[FGL_PLANE_FRAME];
+        f[idx] = col.x, f[n + idx] = col.y, f[2 * n + idx] = col.z;
+    }
+    L.rgb8[idx * 3] = quant8(col.x), L.rgb8[idx * 3 + 1] = quant8(col.y), L.rgb8[idx * 3 + 2] = quant8(col.z);
+}
+
+// ---- quantise / SSAA ---------------------------------------------------------------------------------------------
+__global__ void k_quantize(const float* frame, size_t n, uint8_t* rgb8)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rgb8[i * 3] = quant8(frame[i]), rgb8[i * 3 + 1] = quant8(frame[n + i]), rgb8[i * 3 + 2] = quant8(frame[2 * n + i]);
+}
+
+// render.cpp:291-343: k x k integer box over the quantised image; int sum / float(k*k), truncated
+__global__ void k_ssaa(const uint8_t* rgb8, int W, int H, int k, uint8_t* out, int orow0, int orow1)
+{
+    int ow = W / k;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = orow0 + blockIdx.y;
+    if (x >= ow || y >= orow1) return;
+    int R = 0, G = 0, B = 0;
+    for (int j = 0; j < k; ++j)
+        for (int i = 0; i < k; ++i)
+        {
+            const uint8_t* p = rgb8 + ((size_t)(x * k + i) + (size_t)(y * k + j) * W) * 3;
+            R += p[0], G += p[1], B += p[2];
+        }
+    float kk = (float)(k * k);
+    R = f2i_x86((float)R / kk), G = f2i_x86((float)G / kk), B = f2i_x86((float)B / kk);
+    uint8_t* o = out + ((size_t)x + (size_t)y * ow) * 3;
+    o[0] = (uint8_t)R, o[1] = (uint8_t)G, o[2] = (uint8_t)B;
+}
+
+// ---- in-place two-pass Gaussian (buffer.cpp:59-98) -------------------------------------------------------------------
+// Each pass is the 4th-order recurrence  y[w] = g0 x[w] + sum_i g_i (x[min(w+i, W-1)] + y'[w-i]),  y'[j<0] = a[0]
+// (a[0] is still x[0] while w == 0 and y[0] afterwards), accumulated in the reference's order: centre, then for
+// i = 1..4 the right tap, then the left tap.  Rows (H pass) / columns (V pass) are independent.
+#define BLUR_G0 0.227027f
+#define BLUR_G1 0.1945946f
+#define BLUR_G2 0.1216216f
+#define BLUR_G3 0.054054f
+#define BLUR_G4 0.016216f
+
+struct BlurState
+{
+    float h1, h2, h3, h4;  // y[w-1] .. y[w-4]
+};
+__device__ __forceinline__ float blur_step(BlurState& s, float x0, float x1, float x2, float x3, float x4, bool first)
+{
+    float r = x0 * BLUR_G0;
+    r += x1 * BLUR_G1;
+    r += s.h1 * BLUR_G1;
+    r += x2 * BLUR_G2;
+    r += s.h2 * BLUR_G2;
+    r += x3 * BLUR_G3;
+    r += s.h3 * BLUR_G3;
+    r += x4 * BLUR_G4;
+    r += s.h4 * BLUR_G4;
+    if (first) s.h1 = s.h2 = s.h3 = s.h4 = r;  // from w == 1 on, every clamped left tap reads the new a[0]
+    else s.h4 = s.h3, s.h3 = s.h2, s.h2 = s.h1, s.h1 = r;
+    return r;
+}
+
+constexpr int kBlurTile = 128;
+// H pass: a CTA owns 32 rows; tiles of 128 columns (+4 look-ahead) are staged in shared memory with coalesced loads,
+// one warp (a lane per row) walks the recurrence, the tile is written back coalesced.
+__global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H)
+{
+    __shared__ float tile[32][kBlurTile + 4 + 1];
+    const int row0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BlurState st;
+    st.h1 = st.h2 = st.h3 = st.h4 = 0.f;
+    for (int c0 = 0; c0 < W; c0 += kBlurTile)
+    {
+        int tw = min(kBlurTile, W - c0);
+        for (int r = warp; r < 32; r += 8)
+        {
+            int row = row0 + r;
+            if (row >= H) continue;
+            for (int j = lane; j < tw + 4; j += 32) tile[r][j] = a[(size_t)row * W + min(c0 + j, W - 1)];
+        }
+        __syncthreads();
+        if (warp == 0 && row0 + lane < H)
+        {
+            if (c0 == 0) st.h1 = st.h2 = st.h3 = st.h4 = tile[lane][0];
+            for (int j = 0; j < tw; ++j)
+            {
+                float r = blur_step(st, tile[lane][j], tile[lane][j + 1], tile[lane][j + 2], tile[lane][j + 3], tile[lane][j + 4], c0 + j == 0);
+                tile[lane][j] = r;
+            }
+        }
+        __syncthreads();
+        for (int r = warp; r < 32; r += 8)
+        {
+            int row = row0 + r;
+            if (row >= H) continue;
+            for (int j = lane; j < tw; j += 32) a[(size_t)row * W + c0 + j] = tile[r][j];
+        }
+        __syncthreads();
+    }
+}
+
+// V pass: one thread per column, rows walked in order; loads and stores are coalesced across the warp.
+__global__ void __launch_bounds__(64) k_blur_v(float* a, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    float     x0 = a[x], x1 = a[(size_t)min(1, H - 1) * W + x], x2 = a[(size_t)min(2, H - 1) * W + x], x3 = a[(size_t)min(3, H - 1) * W + x];
+    BlurState st;
+    st.h1 = st.h2 = st.h3 = st.h4 = x0;
+    for (int h = 0; h < H; ++h)
+    {
+        // a[min(h+4, H-1)] is still original: rows below h have not been written yet (at the bottom edge the
+        // clamped taps re-read the not yet overwritten last row, exactly as the in-place loop does)
+        float x4 = (h + 4 <= H - 1) ? a[(size_t)(h + 4) * W + x] : x3;  // x3 already holds the last row when clamping
+        float r = blur_step(st, x0, x1, x2, x3, x4, h == 0);
+        a[(size_t)h * W + x] = r;
+        x0 = x1, x1 = x2, x2 = x3, x3 = x4;
+    }
+}
+
+// ---- SSAO, one warp per pixel: lane = hemisphere sample (render.cpp:229-285) -----------------------------------------
+__global__ void __launch_bounds__(256) k_ssao(SsaoPass S)
+{
+    const size_t n = (size_t)S.W * S.H;
+    const int    lane = threadIdx.x & 31;
+    size_t       idx = (size_t)S.row0 * S.W + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (idx >= (size_t)S.row1 * S.W) return;
+    V3    pos = ld3s(S.worldpos, n, idx), nrm = ld3s(S.normal, n, idx);
+    float fragDepth = S.depth[idx];
+    // accepted unit-ball sample number 32 * pixel + lane of the replayed stream (geometry.h:957-966)
+    const float* b = S.ball + (idx * 32 + lane) * 3;
+    V3           v = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
+    if (!(vdot(v, nrm) > 0.f)) v = v3(-v.x, -v.y, -v.z);  // geometry.h:978-990
+    float sc = vlength(v);
+    sc = (1 - 0.1f) * 1.0f + 0.1f * (sc * sc);  // Lerp(0.1f, 1.0f, sc * sc) with the reference's argument order
+    v = vscale(v, sc);
+    V3 sp = vadd(pos, vscale(v, S.radius));
+    V4 sp4;
+    sp4.x = sp.x, sp4.y = sp.y, sp4.z = sp.z, sp4.w = 1.f;
+    V4        cs = mat4mul(S.viewProj, sp4);
+    V4        ndc = vdivs4(cs, cs.w);
+    V4        ss = mat4mul(S.viewport, ndc);
+    int       sx = f2i_x86(ss.x), sy = f2i_x86(ss.y);
+    long long li = (long long)sx + (long long)sy * S.W;  // unchecked linear index in the reference (buffer.h:37)
+    bool      occ = false;
+    if (li >= 0 && li < (long long)n)
+    {
+        float cached = __ldg(S.depth + li);
+        if (ss.z >= cached + S.bias) occ = S.rangeCheck ? (fabsf(fragDepth - cached) < S.rangeCheckRadius) : true;
+    }
+    int cnt = __popc(__ballot_sync(0xffffffffu, occ));
+    if (lane == 0)
+    {
+        float o = 1.f - (float)cnt * (1.f / 32.f);  // 1/32 steps accumulate exactly
+        S.ao[idx] = (o * o) * o;                    // pow(o, 3): k^3 / 32768 is exact in fp32
+    }
+}
+
+// ---- host accessor helpers -----------------------------------------------------------------------------------------
+__global__ void k_ids(const unsigned long long* vis, size_t n, int* out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = vis[i];
+    out[i] = k == FGL_VIS_EMPTY ? -1 : (int)(unsigned)(k & 0xffffffffull);
+}
+__global__ void k_soa_to_aos(const float* soa, float* aos, size_t n, int ch)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < ch; ++c) aos[i * ch + c] = soa[(size_t)c * n + i];
+}
+__global__ void k_aos_to_soa(const float* aos, float* soa, size_t n, int ch)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < ch; ++c) soa[(size_t)c * n + i] = aos[i * ch + c];
+}
+
+int check_launch(fgl_ctx* c, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return FGL_OK;
+}
+}  // namespace
+
+int fgl_run_fill(fgl_ctx* c, float* dst, size_t n, float value)
+{
+    if (!n) return FGL_OK;
+    LaunchScope ls(c, "fill", n * 4);
+    unsigned    blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_fill<<<blocks, 256, 0, c->stream>>>(dst, n, value);
+    return check_launch(c, "fill");
+}
+
+int fgl_run_fill_rgb(fgl_ctx* c, float* dst, size_t nPixels, const float rgb[3])
+{
+    for (int ch = 0; ch < 3; ++ch)
+        if (int rc = fgl_run_fill(c, dst + ch * nPixels, nPixels, rgb[ch])) return rc;
+    return FGL_OK;
+}
+
+int fgl_run_lighting(fgl_ctx* c, const LightPass& L)
+{
+    size_t   nPix = (size_t)L.W * (L.row1 - L.row0);
+    uint64_t bytes = nPix * (80 + 3 + (L.writeF32 ? 12 : 0));
+    if (!L.shadowOn || L.shadowMode == FGL_SHADOW_HARD)
+    {
+        LaunchScope ls(c, "lighting_hard", bytes);
+        bool        vec = (((size_t)L.W * L.H) % 4 == 0) && (((size_t)L.row0 * L.W) % 4 == 0) && (nPix % 4 == 0);
+        if (vec) k_lighting_hard<4><<<(unsigned)((nPix / 4 + 127) / 128), 128, 0, c->stream>>>(L);
+        else k_lighting_hard<1><<<(unsigned)((nPix + 127) / 128), 128, 0, c->stream>>>(L);
+    }
+    else
+    {
+        LaunchScope ls(c, L.shadowMode == FGL_SHADOW_PCF ? "lighting_pcf" : "lighting_pcss", bytes + nPix * 4);
+        k_lighting_warp<<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(L);
+    }
+    return check_launch(c, "lighting");
+}
+
+int fgl_run_quantize(fgl_ctx* c, const float* frame, size_t nPixels, uint8_t* rgb8)
+{
+    LaunchScope ls(c, "quantize", nPixels * 15);
+    k_quantize<<<(unsigned)((nPixels + 255) / 256), 256, 0, c->stream>>>(frame, nPixels, rgb8);
+    return check_launch(c, "quantize");
+}
+
+int fgl_run_ssaa(fgl_ctx* c, const uint8_t* rgb8, int W, int H, int k, uint8_t* out, int row0, int row1)
+{
+    int ow = W / k, orow0 = row0 / k, orow1 = row1 / k;
+    if (ow <= 0 || orow1 <= orow0) return FGL_OK;
+    LaunchScope ls(c, "ssaa_resolve", (uint64_t)ow * (orow1 - orow0) * (3 * k * k + 3));
+    dim3        grid((ow + 127) / 128, orow1 - orow0);
+    k_ssaa<<<grid, 128, 0, c->stream>>>(rgb8, W, H, k, out, orow0, orow1);
+    return check_launch(c, "ssaa");
+}
+
+int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind)
+{
+    if (kind != FGL_BLUR_TWO_PASS_GAUSSIAN)
+        return fgl_fail(c, FGL_ERR_UNSUPPORTED, "fgl_blur: the in-place 3x3 box (buffer.cpp:35-57) is not on the frame path and has no device kernel yet");
+    size_t n = (size_t)W * H;
+    for (int ch = 0; ch < channels; ++ch)
+    {
+        {
+            LaunchScope ls(c, "blur_h", n * 8);
+            k_blur_h<<<(H + 31) / 32, 256, 0, c->stream>>>(plane + ch * n, W, H);
+        }
+        {
+            LaunchScope ls(c, "blur_v", n * 8);
+            k_blur_v<<<(W + 63) / 64, 64, 0, c->stream>>>(plane + ch * n, W, H);
+        }
+    }
+    return check_launch(c, "blur");
+}
+
+int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S)
+{
+    size_t      nPix = (size_t)S.W * (S.row1 - S.row0);
+    LaunchScope ls(c, "ssao", nPix * (32 + 384));
+    k_ssao<<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(S);
+    return check_launch(c, "ssao");
+}
+
+int fgl_run_ids(fgl_ctx* c, const unsigned long long* vis, size_t n, int* out)
+{
+    LaunchScope ls(c, "ids", n * 12);
+    k_ids<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(vis, n, out);
+    return check_launch(c, "ids");
+}
+
+int fgl_run_aos(fgl_ctx* c, const float* src, float* dst, size_t nPixels, int channels, bool toAos)
+{
+    LaunchScope ls(c, toAos ? "soa_to_aos" : "aos_to_soa", nPixels * channels * 8);
+    if (toAos) k_soa_to_aos<<<(unsigned)((nPixels + 255) / 256), 256, 0, c->stream>>>(src, dst, nPixels, channels);
+    else k_aos_to_soa<<<(unsigned)((nPixels + 255) / 256), 256, 0, c->stream>>>(src, dst, nPixels, channels);
+    return check_launch(c, "layout conversion");
+}

@@ -1,0 +1,589 @@
+// stream.cu — device replay of the reference's global mt19937(5489) sample stream (utility.h:90-103) and the
+// resolution of the PCSS consumption chain (shadow.cpp:92-106).
+//
+// The stream of a frame is a constant: Render::Render starts at draw 0, SSAO (if on) consumes rejection-sampled
+// unit-ball vectors (geometry.h:957-966: 3 draws per candidate, accepted iff x^2+y^2+z^2 < 1), lighting then consumes
+// rejection-sampled unit-disk vectors (geometry.h:968-976: 2 draws per candidate).  Because every candidate uses a
+// fixed number of draws, candidate boundaries are known in advance and acceptance is a parallel predicate; the k-th
+// accepted sample is found with a prefix sum.  The compacted samples are kept in HBM as a table (built once per
+// (seed, pixel count, SSAO on/off) and charged to the consuming pass as read bytes, DESIGN.md "sample stream").
+//
+//   k_mt_checkpoints   single CTA: walks the generator block by block (624 words; three dependent phases of <= 227
+//                      lanes) and stores its state every kCB blocks.
+//   k_mt_generate      one CTA per checkpoint: regenerates kCB blocks of tempered 32-bit draws.
+//   k_count/k_compact  accept flag per candidate, tile sums, scan, ordered compaction into the sample table.
+//
+// PCSS: pixel p (scan order) uses 32 samples and 64 more iff its blocker search found a blocker, so its offset is
+// 32 p + 64 k(p), k(p) = number of earlier pixels with a blocker.  Pixels are first classified with a min/max filter
+// of the shadow map over the search footprint (certainly no blocker / certainly a blocker / uncertain); uncertain
+// pixels are then resolved in scan order in super-chunks of kT pixels: for the t-th pixel of a super-chunk every
+// candidate offset (t + 1 of them) is evaluated in parallel, after which a single thread walks the pixels whose
+// answer actually depends on the offset.
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "stream.h"
+
+namespace
+{
+constexpr int    kMT = 624;
+constexpr int    kCB = 256;                      // generator blocks per checkpoint
+constexpr size_t kWindowCand = (size_t)64 << 20;  // candidates per build window
+constexpr int    kT = 1024;                      // uncertain pixels per super-chunk of the PCSS chain
+constexpr int    kTW = kT / 32;
+
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
+{
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// one generator step for the whole 624-word state: A -> B (blockDim.x threads, all must call)
+__device__ __forceinline__ void mt_twist(const uint32_t* A, uint32_t* B)
+{
+    for (int i = threadIdx.x; i < 227; i += blockDim.x) B[i] = A[i + 397] ^ mt_mix(A[i], A[i + 1]);
+    __syncthreads();
+    for (int i = 227 + threadIdx.x; i < 454; i += blockDim.x) B[i] = B[i - 227] ^ mt_mix(A[i], A[i + 1]);
+    __syncthreads();
+    for (int i = 454 + threadIdx.x; i < kMT; i += blockDim.x) B[i] = B[i - 227] ^ mt_mix(A[i], i == kMT - 1 ? B[0] : A[i + 1]);
+    __syncthreads();
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// ckpt[j] = generator state before block j * kCB is produced.  Extends [have, want).
+__global__ void __launch_bounds__(256) k_mt_checkpoints(uint32_t* ckpt, long long have, long long want)
+{
+    __shared__ uint32_t s[2][kMT];
+    for (int i = threadIdx.x; i < kMT; i += blockDim.x) s[0][i] = ckpt[(have - 1) * kMT + i];
+    __syncthreads();
+    int cur = 0;
+    for (long long ck = have; ck < want; ++ck)
+    {
+        for (int b = 0; b < kCB; ++b)
+        {
+            mt_twist(s[cur], s[cur ^ 1]);
+            cur ^= 1;
+        }
+        for (int i = threadIdx.x; i < kMT; i += blockDim.x) ckpt[ck * kMT + i] = s[cur][i];
+    }
+}
+
+// out[(c * kCB + b) * 624 + i] = draw number ((firstCk + c) * kCB + b) * 624 + i of the stream
+__global__ void __launch_bounds__(256) k_mt_generate(const uint32_t* ckpt, long long firstCk, long long nBlocks, uint32_t* out)
+{
+    __shared__ uint32_t s[2][kMT];
+    long long           c = blockIdx.x;
+    for (int i = threadIdx.x; i < kMT; i += blockDim.x) s[0][i] = ckpt[(firstCk + c) * kMT + i];
+    __syncthreads();
+    int cur = 0;
+    for (int b = 0; b < kCB; ++b)
+    {
+        long long blk = c * kCB + b;
+        if (blk >= nBlocks) break;
+        mt_twist(s[cur], s[cur ^ 1]);
+        cur ^= 1;
+        for (int i = threadIdx.x; i < kMT; i += blockDim.x) out[blk * kMT + i] = mt_temper(s[cur][i]);
+    }
+}
+
+// geometry.h:952-976 with g++'s right-to-left evaluation of constructor arguments:
+// ball: draw0 -> z, draw1 -> y, draw2 -> x; disk: draw0 -> y, draw1 -> x.
+template <int K>
+__device__ __forceinline__ bool candidate(const uint32_t* raw, size_t cand, float& x, float& y, float& z)
+{
+    const uint32_t* r = raw + cand * K;
+    if (K == 3)
+    {
+        z = random_m1p1(r[0]), y = random_m1p1(r[1]), x = random_m1p1(r[2]);
+        return !(x * x + y * y + z * z >= 1.f);
+    }
+    y = random_m1p1(r[0]), x = random_m1p1(r[1]), z = 0.f;
+    return !(x * x + y * y + 0.f * 0.f >= 1.f);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_count(const uint32_t* raw, size_t nCand, int* tileCounts)
+{
+    typedef cub::BlockReduce<int, 256> Reduce;
+    __shared__ typename Reduce::TempStorage tmp;
+    size_t cand = (size_t)blockIdx.x * 256 + threadIdx.x;
+    float  x, y, z;
+    int    a = cand < nCand ? (int)candidate<K>(raw, cand, x, y, z) : 0;
+    int    sum = Reduce(tmp).Sum(a);
+    if (threadIdx.x == 0) tileCounts[blockIdx.x] = sum;
+}
+
+// Writes the accepted samples of this window at their global ordinal (accBase + rank inside the window) while the
+// ordinal is below `need`; the thread that writes ordinal need - 1 records where the stream stands afterwards.
+template <int K>
+__global__ void __launch_bounds__(256) k_compact(const uint32_t* raw, size_t nCand, const int* tileOffsets, const unsigned long long* accBase,
+                                                 unsigned long long need, float* out, unsigned long long rawBase, unsigned long long* rawEnd)
+{
+    typedef cub::BlockScan<int, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    size_t cand = (size_t)blockIdx.x * 256 + threadIdx.x;
+    float  x = 0.f, y = 0.f, z = 0.f;
+    int    a = cand < nCand ? (int)candidate<K>(raw, cand, x, y, z) : 0;
+    int    rank;
+    Scan(tmp).ExclusiveSum(a, rank);
+    if (!a) return;
+    unsigned long long g = *accBase + (unsigned long long)tileOffsets[blockIdx.x] + (unsigned long long)rank;
+    if (g >= need) return;
+    if (K == 3) out[g * 3] = x, out[g * 3 + 1] = y, out[g * 3 + 2] = z;
+    else out[g * 2] = x, out[g * 2 + 1] = y;
+    if (g == need - 1) *rawEnd = rawBase + (unsigned long long)K * (cand + 1);
+}
+__global__ void k_acc_add(unsigned long long* acc, const int* total) { *acc += (unsigned long long)*total; }
+
+// ---- PCSS chain ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fix_depth(float d) { return ((double)d < 0.001) ? 1.f : d; }  // shadow.cpp:33-34
+
+// separable box min / max of the fixed-up shadow map, radius r
+__global__ void k_minmax_h(const float* sm, int W, int H, int r, float* omin, float* omax)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    float mn = __int_as_float(0x7f800000), mx = -mn;
+    for (int i = max(0, x - r); i <= min(W - 1, x + r); ++i)
+    {
+        float d = fix_depth(__ldg(sm + (size_t)y * W + i));
+        mn = fminf(mn, d), mx = fmaxf(mx, d);
+    }
+    omin[(size_t)y * W + x] = mn, omax[(size_t)y * W + x] = mx;
+}
+__global__ void k_minmax_v(const float* imin, const float* imax, int W, int H, int r, float* omin, float* omax)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    float mn = __int_as_float(0x7f800000), mx = -mn;
+    for (int j = max(0, y - r); j <= min(H - 1, y + r); ++j)
+    {
+        mn = fminf(mn, __ldg(imin + (size_t)j * W + x)), mx = fmaxf(mx, __ldg(imax + (size_t)j * W + x));
+    }
+    omin[(size_t)y * W + x] = mn, omax[(size_t)y * W + x] = mx;
+}
+
+struct ChainPass
+{
+    int          W, H;  // frame
+    const float *worldpos, *normal, *lndc;
+    float        lightPos[3], biasSlope, biasMin;
+    ShadowMapD   sm;
+    const float *smMin, *smMax;
+    int          r;
+    float        fsF;  // (float)pcss filter size: |tap offset| <= fsF
+};
+
+// per pixel: shadow coordinate + bias (shadow.cpp:109-118) and the blocker-search class
+__global__ void __launch_bounds__(256) k_classify(ChainPass P, float4* sc4, int* isU, int* isC1)
+{
+    size_t n = (size_t)P.W * P.H, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    V3    pos = v3(P.worldpos[idx], P.worldpos[n + idx], P.worldpos[2 * n + idx]);
+    V3    nrm = v3(P.normal[idx], P.normal[n + idx], P.normal[2 * n + idx]);
+    V3    ln = v3(P.lndc[idx], P.lndc[n + idx], P.lndc[2 * n + idx]);
+    V3    lightDir = vnormalize(vsub(v3(P.lightPos[0], P.lightPos[1], P.lightPos[2]), pos));
+    V3    sc = vadd(vscale(ln, 0.5f), v3(0.5f, 0.5f, 0.5f));
+    float bias = fmaxf(P.biasSlope * (1.f - vdot(nrm, lightDir)), P.biasMin);
+    sc4[idx] = make_float4(sc.x, sc.y, sc.z, bias);
+
+    // every tap lands at u in [ulo, uhi] (the float add is monotone in the offset, |offset| <= fsF)
+    float ulo = sc.x + (-P.fsF), uhi = sc.x + P.fsF, vlo = sc.y + (-P.fsF), vhi = sc.y + P.fsF;
+    int   cls = 2;
+    if (uhi < 0.f || ulo > 1.f || vhi < 0.f || vlo > 1.f) cls = 0;  // all taps outside the map: +inf, never a blocker
+    else if (ulo == ulo && vlo == vlo && sc.z == sc.z)
+    {
+        bool  mayOut = ulo < 0.f || uhi > 1.f || vlo < 0.f || vhi > 1.f;
+        float cu = clampf(sc.x, 0.f, 1.f), cv = clampf(sc.y, 0.f, 1.f);
+        int   cx = f2i_x86((float)P.sm.iw * cu), cy = f2i_x86((float)P.sm.ih * cv);
+        int   x0 = f2i_x86((float)P.sm.iw * fmaxf(ulo, 0.f)), x1 = f2i_x86((float)P.sm.iw * fminf(uhi, 1.f));
+        int   y0 = f2i_x86((float)P.sm.ih * fmaxf(vlo, 0.f)), y1 = f2i_x86((float)P.sm.ih * fminf(vhi, 1.f));
+        if (x0 >= cx - P.r && x1 <= cx + P.r && y0 >= cy - P.r && y1 <= cy + P.r && cx >= 0 && cx < P.sm.w && cy >= 0 && cy < P.sm.h)
+        {
+            float dmin = P.smMin[(size_t)cy * P.sm.w + cx], dmax = P.smMax[(size_t)cy * P.sm.w + cx];
+            if (!mayOut && sc.z > dmax + bias) cls = 1;       // every tap blocks
+            else if (!(sc.z > dmin + bias)) cls = 0;           // no tap can block
+        }
+    }
+    isU[idx] = cls == 2, isC1[idx] = cls == 1;
+}
+
+// uncertain pixels, in scan order: pixel index, number of certain blockers before it, shadow coordinate + bias
+__global__ void __launch_bounds__(256) k_gather_uncertain(size_t n, const int* isU, const int* posU, const int* c1pre, const float4* sc4, unsigned* Upix,
+                                                          unsigned* Uc1, float4* Usc)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n || !isU[idx]) return;
+    int j = posU[idx];
+    Upix[j] = (unsigned)idx, Uc1[j] = (unsigned)c1pre[idx], Usc[j] = sc4[idx];
+}
+
+// blocker flag of one pixel for one candidate chunk: any of the 32 taps blocks (shadow.cpp:65-90)
+__device__ __forceinline__ bool blocker_any(const ShadowMapD& sm, const float2* disk, double fs, float4 s, size_t chunk, int lane)
+{
+    float2 d = __ldg(disk + chunk * 32 + lane);
+    float  ox = (float)((double)d.x * fs), oy = (float)((double)d.y * fs);
+    float  sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
+    return __any_sync(0xffffffffu, s.z > sampleDepth + s.w);
+}
+
+// Super-chunk [j0, j0 + kT) of the uncertain list: bit d of row t = blocker flag of pixel j0 + t if d of the t
+// uncertain pixels before it in this super-chunk have blockers.  One warp per 32-bit word.
+__global__ void __launch_bounds__(256) k_chain_eval(int j0, int nU, const unsigned* mState, const unsigned* Upix, const unsigned* Uc1, const float4* Usc,
+                                                    ShadowMapD sm, const float2* disk, double fs, uint32_t* bits)
+{
+    int lane = threadIdx.x & 31;
+    int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (task >= 16 * kTW * (kTW + 1)) return;
+    int g = 0;
+    while (16 * (g + 1) * (g + 2) <= task) ++g;  // rows 32g .. 32g+31 have g + 1 words each
+    int rem = task - 16 * g * (g + 1);
+    int t = 32 * g + rem / (g + 1), word = rem % (g + 1);
+    int j = j0 + t;
+    if (j >= nU) return;
+    unsigned m0 = *mState;
+    size_t   p = Upix[j];
+    size_t   kbase = (size_t)Uc1[j] + m0 + 32 * word;
+    float4   s = Usc[j];
+    int      dmax = min(31, t - 32 * word);
+    uint32_t w = 0;
+#pragma unroll 4
+    for (int d = 0; d <= dmax; ++d)
+    {
+        bool f = blocker_any(sm, disk, fs, s, p + 2 * (kbase + d), lane);
+        w |= (f ? 1u : 0u) << d;
+    }
+    if (lane == 0) bits[t * kTW + word] = w;
+}
+
+// One CTA: finds the pixels of the super-chunk whose flag depends on the offset, walks them serially from shared
+// memory, writes every pixel's flag and advances the chain state.
+__global__ void __launch_bounds__(kT) k_chain_walk(int j0, int nU, unsigned* mState, const uint32_t* bits, uint8_t* flagU)
+{
+    typedef cub::BlockScan<int, kT> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int      cpre[kT];      // constants (insensitive pixels with a blocker) before row t
+    __shared__ short    sens[kT];      // compacted rows that depend on the offset
+    __shared__ uint8_t  flag[kT];
+    __shared__ int      nSens, total;
+    extern __shared__ uint32_t rows[];  // nSens x kTW words
+
+    int  t = threadIdx.x, j = j0 + t;
+    bool live = j < nU;
+    int  isConst = 1, val = 0;
+    if (live)
+    {
+        int      words = t / 32 + 1;
+        uint32_t lastMask = (t % 32 == 31) ? 0xffffffffu : ((1u << (t % 32 + 1)) - 1u);
+        bool     all0 = true, all1 = true;
+        for (int w = 0; w < words; ++w)
+        {
+            uint32_t b = bits[t * kTW + w], m = (w == words - 1) ? lastMask : 0xffffffffu;
+            all0 &= (b & m) == 0, all1 &= (b & m) == m;
+        }
+        isConst = all0 || all1, val = all1 ? 1 : 0;
+    }
+    int cp, sp;
+    Scan(tmp).ExclusiveSum(isConst ? val : 0, cp);
+    __syncthreads();
+    Scan(tmp).ExclusiveSum(isConst ? 0 : 1, sp);
+    cpre[t] = cp;
+    flag[t] = (uint8_t)val;
+    if (!isConst)
+    {
+        sens[sp] = (short)t;
+        for (int w = 0; w < kTW; ++w) rows[sp * kTW + w] = w <= t / 32 ? bits[t * kTW + w] : 0u;
+    }
+    if (t == kT - 1) nSens = sp + (isConst ? 0 : 1), total = cp + (isConst ? val : 0);
+    __syncthreads();
+    if (t == 0)
+    {
+        int ms = 0;  // sensitive pixels with a blocker so far
+        for (int i = 0; i < nSens; ++i)
+        {
+            int      row = sens[i];
+            int      d = cpre[row] + ms;
+            uint32_t b = (rows[i * kTW + (d >> 5)] >> (d & 31)) & 1u;
+            flag[row] = (uint8_t)b;
+            ms += (int)b;
+        }
+        *mState += (unsigned)(total + ms);
+    }
+    __syncthreads();
+    if (live) flagU[j] = flag[t];
+}
+
+__global__ void __launch_bounds__(256) k_pixel_flags(size_t n, const int* isU, const int* isC1, const int* posU, const uint8_t* flagU, int* hasBlocker)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    hasBlocker[idx] = isU[idx] ? (int)flagU[posU[idx]] : isC1[idx];
+}
+__global__ void __launch_bounds__(256) k_chunk_index(size_t n, const int* kpre, unsigned* chunkOf)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    chunkOf[idx] = (unsigned)idx + 2u * (unsigned)kpre[idx];
+}
+}  // namespace
+
+// ====================================================================================================================
+struct SampleStream
+{
+    DevBuf    ckpt;
+    long long nCkpt = 0;  // checkpoints 0 .. nCkpt-1 exist
+    DevBuf    window, tileCounts, tileOffsets, counters;
+    // tables
+    DevBuf             ball, disk;
+    unsigned long long ballNeed = 0, ballRawEnd = 0;  // ball table holds ballNeed samples; the stream then stands at ballRawEnd
+    unsigned long long diskNeed = 0, diskRawBegin = ~0ull;
+    // frame state
+    bool               ssaoThisFrame = false;
+    unsigned long long ssaoSamples = 0;
+    // chain scratch
+    DevBuf smTmpMin, smTmpMax, smMin, smMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, bits, flagU, hasB, kpre, chunkOf, mState;
+};
+
+static SampleStream* S_of(fgl_ctx* c)
+{
+    if (!c->stream_state) c->stream_state = new SampleStream();
+    return c->stream_state;
+}
+
+void fgl_stream_destroy(fgl_ctx* c)
+{
+    SampleStream* s = c->stream_state;
+    if (!s) return;
+    DevBuf* all[] = { &s->ckpt, &s->window, &s->tileCounts, &s->tileOffsets, &s->counters, &s->ball, &s->disk, &s->smTmpMin, &s->smTmpMax, &s->smMin,
+                      &s->smMax, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
+                      &s->chunkOf, &s->mState };
+    for (DevBuf* b : all)
+        if (b->p) cudaFree(b->p);
+    delete s;
+    c->stream_state = nullptr;
+}
+
+void fgl_stream_begin_frame(fgl_ctx* c)
+{
+    SampleStream* s = S_of(c);
+    s->ssaoThisFrame = false;
+    s->ssaoSamples = 0;
+}
+
+static int ensure_checkpoints(fgl_ctx* c, SampleStream* s, long long wantCk)
+{
+    if (wantCk <= s->nCkpt) return FGL_OK;
+    wantCk += wantCk / 8 + 64;  // amortise
+    if (int rc = fgl_reserve(c, s->ckpt, (size_t)wantCk * kMT * 4)) return rc;
+    if (s->nCkpt == 0)
+    {   // std::mt19937 default seed (utility.h:92: a default-constructed engine)
+        std::vector<uint32_t> st(kMT);
+        st[0] = 5489u;
+        for (int i = 1; i < kMT; ++i) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+        FGL_CUDA(c, cudaMemcpyAsync(s->ckpt.p, st.data(), kMT * 4, cudaMemcpyHostToDevice, c->stream));
+        FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+        s->nCkpt = 1;
+    }
+    {
+        LaunchScope ls(c, "mt_checkpoints", 0);
+        k_mt_checkpoints<<<1, 256, 0, c->stream>>>((uint32_t*)s->ckpt.p, s->nCkpt, wantCk);
+    }
+    s->nCkpt = wantCk;
+    return FGL_OK;
+}
+
+// Builds a table of `need` accepted samples (K = 3: unit ball, K = 2: unit disk) starting at draw rawBegin.
+template <int K>
+static int build_table(fgl_ctx* c, SampleStream* s, DevBuf& table, unsigned long long rawBegin, unsigned long long need, unsigned long long* rawEndOut)
+{
+    if (int rc = fgl_reserve(c, table, (size_t)need * K * 4 + 16)) return rc;
+    if (int rc = fgl_reserve(c, s->counters, 64)) return rc;
+    unsigned long long* dAcc = (unsigned long long*)s->counters.p;
+    unsigned long long* dRawEnd = dAcc + 1;
+    FGL_CUDA(c, cudaMemsetAsync(s->counters.p, 0, 64, c->stream));
+    const double       rate = K == 3 ? 0.5235987 : 0.7853981;
+    unsigned long long acc = 0, candDone = 0;
+    while (acc < need)
+    {
+        unsigned long long remaining = need - acc;
+        size_t             nCand = (size_t)std::min<double>((double)kWindowCand, remaining / rate * 1.002 + 65536.0);
+        unsigned long long r0 = rawBegin + (unsigned long long)K * candDone, r1 = r0 + (unsigned long long)K * nCand;
+        long long          firstCk = (long long)(r0 / kMT / kCB);
+        long long          lastBlock = (long long)((r1 + kMT - 1) / kMT);  // exclusive
+        long long          nCk = (lastBlock + kCB - 1) / kCB - firstCk;
+        long long          nBlocks = lastBlock - firstCk * kCB;
+        if (int rc = ensure_checkpoints(c, s, firstCk + nCk)) return rc;
+        if (int rc = fgl_reserve(c, s->window, (size_t)nCk * kCB * kMT * 4)) return rc;
+        {
+            LaunchScope ls(c, "mt_generate", (uint64_t)nBlocks * kMT * 4);
+            k_mt_generate<<<(unsigned)nCk, 256, 0, c->stream>>>((const uint32_t*)s->ckpt.p, firstCk, nBlocks, (uint32_t*)s->window.p);
+        }
+        const uint32_t* raw = (const uint32_t*)s->window.p + (r0 - (unsigned long long)firstCk * kCB * kMT);
+        size_t          nTiles = (nCand + 255) / 256;
+        if (int rc = fgl_reserve(c, s->tileCounts, (nTiles + 1) * 4)) return rc;
+        if (int rc = fgl_reserve(c, s->tileOffsets, (nTiles + 1) * 4)) return rc;
+        FGL_CUDA(c, cudaMemsetAsync((int*)s->tileCounts.p + nTiles, 0, 4, c->stream));
+        {
+            LaunchScope ls(c, "stream_count", (uint64_t)nCand * K * 4);
+            k_count<K><<<(unsigned)nTiles, 256, 0, c->stream>>>(raw, nCand, (int*)s->tileCounts.p);
+        }
+        size_t tmpBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (int*)s->tileCounts.p, (int*)s->tileOffsets.p, (int)nTiles + 1, c->stream);
+        if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
+        {
+            LaunchScope ls(c, "scan", nTiles * 8);
+            cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, (int*)s->tileCounts.p, (int*)s->tileOffsets.p, (int)nTiles + 1, c->stream);
+        }
+        {
+            LaunchScope ls(c, "stream_compact", (uint64_t)nCand * K * 4);
+            k_compact<K><<<(unsigned)nTiles, 256, 0, c->stream>>>(raw, nCand, (const int*)s->tileOffsets.p, dAcc, need, (float*)table.p, r0, dRawEnd);
+        }
+        ++c->launches;
+        k_acc_add<<<1, 1, 0, c->stream>>>(dAcc, (const int*)s->tileOffsets.p + nTiles);
+        unsigned long long host[2];
+        FGL_CUDA(c, cudaMemcpyAsync(host, s->counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+        acc = host[0];
+        if (acc >= need && rawEndOut) *rawEndOut = host[1];
+        candDone += nCand;
+    }
+    return FGL_OK;
+}
+
+int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S)
+{
+    SampleStream*      s = S_of(c);
+    unsigned long long need = (unsigned long long)S.W * S.H * 32;
+    if (s->ballNeed != need)
+    {
+        s->ballNeed = 0;
+        if (int rc = build_table<3>(c, s, s->ball, 0, need, &s->ballRawEnd)) return rc;
+        s->ballNeed = need;
+    }
+    S.ball = (const float*)s->ball.p;
+    s->ssaoThisFrame = true, s->ssaoSamples = need;
+    return FGL_OK;
+}
+
+static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
+{
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, in, out, (int)n, c->stream);
+    if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
+    LaunchScope ls(c, "scan", n * 8);
+    cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, in, out, (int)n, c->stream);
+    return FGL_OK;
+}
+
+int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
+{
+    SampleStream*      s = S_of(c);
+    size_t             n = (size_t)L.W * L.H;
+    unsigned long long rawBegin = s->ssaoThisFrame ? s->ballRawEnd : 0ull;
+    // PCF: 64 samples per pixel; PCSS: chunk index <= 3 n, plus the 96 samples of the last pixel
+    unsigned long long need = L.shadowMode == FGL_SHADOW_PCF ? (unsigned long long)n * 64 : ((unsigned long long)n * 3 + 4) * 32;
+    if (s->diskRawBegin != rawBegin || s->diskNeed < need)
+    {
+        s->diskNeed = 0;
+        if (int rc = build_table<2>(c, s, s->disk, rawBegin, need, nullptr)) return rc;
+        s->diskNeed = need, s->diskRawBegin = rawBegin;
+    }
+    L.disk = (const float2*)s->disk.p;
+    L.chunkOf = nullptr;
+    if (L.shadowMode == FGL_SHADOW_PCF) return FGL_OK;
+
+    // ---- PCSS chain --------------------------------------------------------------------------------------------
+    cudaStream_t st = c->stream;
+    size_t       smN = (size_t)L.sm.w * L.sm.h;
+    DevBuf*      f4[] = { &s->smTmpMin, &s->smTmpMax, &s->smMin, &s->smMax };
+    for (DevBuf* b : f4)
+        if (int rc = fgl_reserve(c, *b, smN * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->sc4, n * 16)) return rc;
+    DevBuf* i4[] = { &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->hasB, &s->kpre };
+    for (DevBuf* b : i4)
+        if (int rc = fgl_reserve(c, *b, (n + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->chunkOf, n * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->mState, 16)) return rc;
+    if (int rc = fgl_reserve(c, s->bits, (size_t)kT * kTW * 4)) return rc;
+
+    float fsF = (float)L.pcssFilter;
+    if (!((double)fsF >= L.pcssFilter)) fsF = nextafterf(fsF, 1e30f);  // |(float)(d * fs)| <= fsF for |d| < 1
+    int r = (int)ceil((double)L.sm.iw * (double)fsF) + 1;
+    {
+        LaunchScope ls(c, "pcss_minmax", smN * 24);
+        dim3        grid((L.sm.w + 127) / 128, L.sm.h);
+        k_minmax_h<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, r, (float*)s->smTmpMin.p, (float*)s->smTmpMax.p);
+        ++c->launches;
+        k_minmax_v<<<grid, 128, 0, st>>>((const float*)s->smTmpMin.p, (const float*)s->smTmpMax.p, L.sm.w, L.sm.h, r, (float*)s->smMin.p, (float*)s->smMax.p);
+    }
+    ChainPass P;
+    P.W = L.W, P.H = L.H;
+    P.worldpos = L.planes.p[FGL_PLANE_WORLDPOS], P.normal = L.planes.p[FGL_PLANE_NORMAL], P.lndc = L.planes.p[FGL_PLANE_LIGHTNDC];
+    memcpy(P.lightPos, L.lightPos, 12);
+    P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
+    P.smMin = (const float*)s->smMin.p, P.smMax = (const float*)s->smMax.p, P.r = r, P.fsF = fsF;
+    unsigned nb = (unsigned)((n + 255) / 256);
+    {
+        LaunchScope ls(c, "pcss_classify", n * (36 + 16 + 8));
+        k_classify<<<nb, 256, 0, st>>>(P, (float4*)s->sc4.p, (int*)s->isU.p, (int*)s->isC1.p);
+    }
+    FGL_CUDA(c, cudaMemsetAsync((int*)s->isU.p + n, 0, 4, st));
+    if (int rc = scan_ints(c, (const int*)s->isU.p, (int*)s->posU.p, n + 1)) return rc;
+    if (int rc = scan_ints(c, (const int*)s->isC1.p, (int*)s->c1pre.p, n)) return rc;
+    int nU = 0;
+    FGL_CUDA(c, cudaMemcpyAsync(&nU, (int*)s->posU.p + n, 4, cudaMemcpyDeviceToHost, st));
+    FGL_CUDA(c, cudaStreamSynchronize(st));
+    if (int rc = fgl_reserve(c, s->Upix, (size_t)(nU + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->Uc1, (size_t)(nU + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->Usc, (size_t)(nU + 1) * 16)) return rc;
+    if (int rc = fgl_reserve(c, s->flagU, (size_t)nU + 16)) return rc;
+    if (nU > 0)
+    {
+        {
+            LaunchScope ls(c, "pcss_gather", n * 12);
+            k_gather_uncertain<<<nb, 256, 0, st>>>(n, (const int*)s->isU.p, (const int*)s->posU.p, (const int*)s->c1pre.p, (const float4*)s->sc4.p,
+                                                   (unsigned*)s->Upix.p, (unsigned*)s->Uc1.p, (float4*)s->Usc.p);
+        }
+        FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 16, st));
+        const int evalWarps = 16 * kTW * (kTW + 1);
+        for (int j0 = 0; j0 < nU; j0 += kT)
+        {
+            {
+                LaunchScope ls(c, "pcss_chain_eval", 0);
+                k_chain_eval<<<(evalWarps * 32 + 255) / 256, 256, 0, st>>>(j0, nU, (const unsigned*)s->mState.p, (const unsigned*)s->Upix.p,
+                                                                           (const unsigned*)s->Uc1.p, (const float4*)s->Usc.p, L.sm, L.disk, L.pcssFilter,
+                                                                           (uint32_t*)s->bits.p);
+            }
+            {
+                static bool attr = false;
+                if (!attr)
+                {
+                    FGL_CUDA(c, cudaFuncSetAttribute(k_chain_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kTW * 4));
+                    attr = true;
+                }
+                LaunchScope ls(c, "pcss_chain_walk", 0);
+                k_chain_walk<<<1, kT, (size_t)kT * kTW * 4, st>>>(j0, nU, (unsigned*)s->mState.p, (const uint32_t*)s->bits.p, (uint8_t*)s->flagU.p);
+            }
+        }
+    }
+    {
+        LaunchScope ls(c, "pcss_flags", n * 16);
+        k_pixel_flags<<<nb, 256, 0, st>>>(n, (const int*)s->isU.p, (const int*)s->isC1.p, (const int*)s->posU.p, (const uint8_t*)s->flagU.p, (int*)s->hasB.p);
+    }
+    if (int rc = scan_ints(c, (const int*)s->hasB.p, (int*)s->kpre.p, n)) return rc;
+    {
+        LaunchScope ls(c, "pcss_chunk_index", n * 8);
+        k_chunk_index<<<nb, 256, 0, st>>>(n, (const int*)s->kpre.p, (unsigned*)s->chunkOf.p);
+    }
+    L.chunkOf = (const unsigned*)s->chunkOf.p;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("pcss chain: ") + cudaGetErrorString(e));
+    return FGL_OK;
+}

@@ -1,0 +1,13 @@
+// stream.h — replay of the reference's single global mt19937 sample stream (utility.h:90-103) on the device.
+#pragma once
+#include "fgl_internal.h"
+
+void fgl_stream_destroy(fgl_ctx* c);
+// Render::Render starts a frame at stream position 0 (the reference process renders exactly one frame).
+void fgl_stream_begin_frame(fgl_ctx* c);
+// SSAO consumes the stream first (render.cpp:204-209): pixel p takes accepted unit-ball samples 32p .. 32p+31.
+int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S);
+// Deferred lighting continues where SSAO stopped: PCF takes 64 accepted unit-disk samples per pixel, PCSS 32 plus
+// 64 more iff the pixel's blocker search found a blocker (shadow.cpp:92-106) — a frame-long dependency chain that
+// is resolved here into a per-pixel chunk index.
+int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L);

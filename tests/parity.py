@@ -1,0 +1,113 @@
+"""Shared helpers of the parity tests: run the reference / oracle / CUDA path on a scene, compare planes."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from forkerrenderer_b200 import binding as B  # noqa: E402
+
+ASSETS = os.path.join(REPO, "oracle", "_ref", "assets")
+REF_DRIVER = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+ORACLE_LIB = os.path.join(REPO, "oracle", "liboracle.so")
+ORACLE_HOST_LIB = os.path.join(REPO, "oracle", "liboracle_host.so")
+
+F32_PLANES = ["depth", "shadow", "normal", "worldpos", "lightndc", "albedo", "emissive", "param", "shadingtype", "ao", "frame"]
+
+# scene id -> (scene file, shadow mode, wrap, filter)
+CONFIGS = {
+    "c1_hard": ("scenes/c1.scene", "hard", 0, 0),
+    "c1_pcf": ("scenes/c1.scene", "pcf", 0, 0),
+    "c1_pcss": ("scenes/c1.scene", "pcss", 0, 0),
+    "c1_ssao_pcss": ("scenes/c1_ssao.scene", "pcss", 0, 0),
+    "c2_pcf": ("scenes/c2.scene", "pcf", 0, 0),
+    "c2_hard": ("scenes/c2.scene", "hard", 0, 0),
+    "c3_pcss_ssao": ("scenes/c3.scene", "pcss", 0, 0),
+    "c4_hard": ("scenes/c4.scene", "hard", 0, 0),
+    "c4_catbox_linear": ("scenes/c4_catbox.scene", "hard", 1, 1),
+    "pbr_hard": ("scenes/pbr.scene", "hard", 0, 0),
+}
+
+
+def have_ref():
+    return os.path.exists(REF_DRIVER) and os.path.isdir(os.path.join(ASSETS, "obj"))
+
+
+def run_reference(cfg, out_dir=None, ids=True):
+    """Runs the UNMODIFIED reference (oracle/_ref/ref_driver) and returns {plane: array} + meta."""
+    scene, shadow, wrap, filt = CONFIGS[cfg]
+    out_dir = out_dir or os.path.join(tempfile.gettempdir(), "fgl_ref_" + cfg)
+    os.makedirs(out_dir, exist_ok=True)
+    meta_path = os.path.join(out_dir, "meta.json")
+    if not os.path.exists(meta_path):
+        cmd = [REF_DRIVER, "--assets", ASSETS, "--scene", os.path.join(REPO, scene), "--out", out_dir, "--shadow", shadow,
+               "--wrap", str(wrap), "--filter", str(filt), "--quiet"] + (["--ids"] if ids else [])
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    meta = json.load(open(meta_path))
+    W, H = meta["width"], meta["height"]
+    out = {"meta": meta}
+    for name in F32_PLANES:
+        p = os.path.join(out_dir, name + ".f32")
+        if os.path.exists(p):
+            a = np.fromfile(p, dtype=np.float32)
+            out[name] = a.reshape(H, W, 3) if a.size == W * H * 3 else a.reshape(H, W)
+    out["frame_u8"] = np.fromfile(os.path.join(out_dir, "frame.u8"), dtype=np.uint8).reshape(H, W, 3)
+    p = os.path.join(out_dir, "ssaa.u8")
+    if os.path.exists(p):
+        out["ssaa_u8"] = np.fromfile(p, dtype=np.uint8).reshape(meta["out_height"], meta["out_width"], 3)
+    for name in ("ids_camera", "ids_light"):
+        p = os.path.join(out_dir, name + ".i32")
+        if os.path.exists(p):
+            out[name] = np.fromfile(p, dtype=np.int32).reshape(H, W)
+    return out
+
+
+def render_host(host, cfg, planes=None, materialize=True):
+    """Renders a config through a Host facade (product or oracle-linked) and reads the planes back."""
+    scene, shadow, wrap, filt = CONFIGS[cfg]
+    sc = host.load_scene(os.path.join(REPO, scene), ASSETS, wrap, filt)
+    try:
+        host.render(sc, shadow, materialize)
+        f = host.fgl
+        names = planes or (["depth", "shadow", "frame", "frame_u8", "ids_camera", "ids_light"] +
+                           (["normal", "worldpos", "lightndc", "albedo", "emissive", "param", "shadingtype", "ao"] if sc.deferred else []) +
+                           (["ssaa_u8"] if sc.ssaa else []))
+        out = {n: f.read_plane(n) for n in names}
+        out["scene"] = dict(width=sc.width, height=sc.height, triangles=sc.triangles, deferred=sc.deferred)
+        return out
+    finally:
+        sc.free()
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    return bool(np.array_equal(a.view(np.uint8), b.view(np.uint8)))
+
+
+def diff_stats(a, b):
+    """dict with max abs diff, count of differing elements, fraction; ints compared exactly."""
+    if a.shape != b.shape:
+        return dict(shape_mismatch=(a.shape, b.shape))
+    if a.dtype == np.float32:
+        neq = a.view(np.uint32) != b.view(np.uint32)
+        with np.errstate(invalid="ignore", over="ignore"):
+            d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+        d = np.where(np.isfinite(d), d, 0)
+        return dict(n_diff=int(neq.sum()), frac=float(neq.mean()), max_abs=float(d.max()))
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    return dict(n_diff=int((d > 0).sum()), frac=float((d > 0).mean()), max_abs=int(d.max()),
+                frac_gt1=float((d > 1).mean()))
+
+
+def pixel_frac_gt1(a, b):
+    """fraction of PIXELS with any channel differing by more than 1 LSB (the north-star colour criterion)."""
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    if d.ndim == 3:
+        d = d.max(axis=2)
+    return float((d > 1).mean())
