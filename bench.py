@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — frames/s and Mpixels/s of the raster-and-shade frame (Render::Render, reference render.cpp:40-58).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c1_ssao|c4|c5] [--impl ours|reference]
+
+One step = one frame of the workload scene: shadow pass, geometry pass, SSAO + in-place Gaussian, deferred lighting
+with the scene's shadow filter, 8-bit quantise (+ SSAA resolve).  Geometry and textures are resident on the device
+(they are the renderer's "model"; the reference's own stopwatch lines exclude scene loading too).
+
+  value   whole-frame throughput in Mpixels/s (output pixels), device-timed with CUDA events, inputs resident.
+  e2e     the same metric through the reference-facing facade call (frh_render = Render::Preconfigure + Render::Render)
+          including, every step, the host->device copy of the frame's draw commands / uniforms and the device->host
+          read of the finished 8-bit frame into host memory; wall-clock timed around the call + read.
+  roofline   dominant kernel (per-kernel CUDA events from the library's own instrumentation) against the measured HBM
+             copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline   the UNMODIFIED reference (oracle/_ref/ref_driver, single-threaded by construction) on a bounded
+                 sample: the same scene at a reduced resolution, compared in Mpixels/s.
+
+--impl reference times only the CPU reference (rank 0), same metric/unit/config.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (scene file, shadow mode, wrap, filter, description)
+    "c1": ("scenes/c1.scene", "hard", 0, 0, "scenes/c1.scene: Mary + plane, 1280x800 deferred, hard shadow"),
+    "c1_ssao": ("scenes/c1_ssao.scene", "pcss", 0, 0, "scenes/c1_ssao.scene: Mary + plane, 1280x800 deferred, PCSS + SSAO"),
+    "c3": ("scenes/c3.scene", "pcss", 0, 0, "scenes/c3.scene: plane + Mary + diablo_pose + great_sword, 3840x2160 deferred, PCSS + SSAO (two-pass Gaussian)"),
+    "c3_pbr": ("scenes/c3_pbr.scene", "pcss", 0, 0, "scenes/c3_pbr.scene: C3 + chalkboard (Cook-Torrance), 3840x2160 deferred, PCSS + SSAO"),
+    "c4": ("scenes/c4_catbox.scene", "hard", 1, 1, "scenes/c4_catbox.scene: SSAA 2x (2560x1600 raster), Repeat + Linear textures"),
+}
+ASSETS = os.path.join(REPO, "oracle", "_ref", "assets")
+REF_DRIVER = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag, self.proc = gpu_index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def reduced_scene(scene_path, factor):
+    """Same scene at 1/factor of the linear resolution (bounded CPU sample).  Returns (path, width, height)."""
+    txt = open(os.path.join(REPO, scene_path)).read()
+    m = re.search(r"^screen\s+(\d+)\s+(\d+)", txt, re.M)
+    w, h = int(m.group(1)) // factor, int(m.group(2)) // factor
+    txt = re.sub(r"^screen\s+\d+\s+\d+", "screen %d %d" % (w, h), txt, flags=re.M)
+    fd, path = tempfile.mkstemp(suffix=".scene", prefix="fgl_bench_")
+    os.write(fd, txt.encode())
+    os.close(fd)
+    return path, w, h
+
+
+def time_reference(workload, frames, factor):
+    """Runs the unmodified reference on the (reduced) scene; returns per-frame seconds and the pixel count."""
+    scene, shadow, wrap, filt, _ = WORKLOADS[workload]
+    if not os.path.exists(REF_DRIVER):
+        raise RuntimeError("oracle/_ref/ref_driver is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists")
+    path, w, h = reduced_scene(scene, factor)
+    out = tempfile.mkdtemp(prefix="fgl_bench_ref_")
+    r = subprocess.run([REF_DRIVER, "--assets", ASSETS, "--scene", path, "--out", out, "--shadow", shadow, "--wrap", str(wrap),
+                        "--filter", str(filt), "--frames", str(frames), "--quiet"], check=True, stdout=subprocess.PIPE, text=True)
+    os.unlink(path)
+    times = [json.loads(l)["t_frame"] for l in r.stdout.splitlines() if l.startswith("{")]
+    return times, w, h
+
+
+def cpu_factor(workload):
+    return {"c3": 4, "c3_pbr": 4, "c1_ssao": 2}.get(workload, 1)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    factor = cpu_factor(args.workload)
+    times, w, h = time_reference(args.workload, args.warmup + args.steps, factor)
+    t = times[args.warmup:]
+    ms = 1e3 * sum(t) / len(t)
+    mpx = w * h / 1e6 / (ms / 1e3)
+    sample = "%s at %dx%d (1/%d linear resolution), %d frames, single thread" % (WORKLOADS[args.workload][0], w, h, factor, len(t))
+    line = {"impl": "reference", "metric": "mpixels_per_s", "value": mpx, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "reference assets (obj/*), synthetic camera/light of the scene file",
+            "config": {"workload": WORKLOADS[args.workload][4], "sample": sample},
+            "frames_per_s": 1e3 / ms,
+            "cpu_baseline": {"value": mpx, "unit": "Mpixels/s", "cores": 1, "kind": "reference", "sample": sample},
+            "e2e": {"value": mpx, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from forkerrenderer_b200 import binding as B
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    os.environ["FGL_DEVICE"] = str(local)
+
+    scene_file, shadow, wrap, filt, desc = WORKLOADS[args.workload]
+    host = B.product_host()
+    fgl = host.fgl
+    sc = host.load_scene(os.path.join(REPO, scene_file), ASSETS, wrap, filt)
+    W, H = sc.width, sc.height
+    out_px = W * H
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        fgl.sync()
+        torch.cuda.synchronize()
+
+    # L2 flush between timed iterations for workloads whose planes could sit in the 126 MB L2
+    plane_bytes = sc.buffer_width * sc.buffer_height * 100
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if plane_bytes < (512 << 20) else None
+
+    def flush_l2():
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+
+    def frame(materialize=False):
+        host.render(sc, shadow, materialize)
+
+    launches0 = fgl.launch_count()
+    for _ in range(args.warmup):
+        frame()
+    barrier()
+
+    # ---- device-timed region: K frames, each bracketed by CUDA events on the library's stream -----------------
+    stream = torch.cuda.Stream()
+    fgl.set_stream(stream.cuda_stream)
+    for _ in range(2):
+        frame()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = fgl.launch_count()
+    ev = []
+    barrier()
+    for _ in range(args.steps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        frame()
+        e1.record(stream)
+        ev.append((e0, e1))
+    barrier()
+    launches = fgl.launch_count() - l0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms = sum(ms_steps) / len(ms_steps)
+
+    # ---- end to end: facade call + read of the 8-bit frame into host memory, wall clock ------------------------
+    h2d = 0
+    e2e_t = []
+    for i in range(args.steps + 1):
+        flush_l2()
+        t0 = time.perf_counter()
+        frame()
+        img = fgl.read_plane("ssaa_u8" if sc.ssaa else "frame_u8")
+        t1 = time.perf_counter()
+        if i:
+            e2e_t.append(t1 - t0)
+    e2e_ms = 1e3 * sum(e2e_t) / len(e2e_t)
+    d2h = int(img.nbytes)
+    n_draws = 0
+    clocks = sampler.finish()
+
+    # ---- per-kernel breakdown (library instrumentation, separate frames) -----------------------------------------
+    fgl.enable_timing(True)
+    fgl.reset_timings()
+    nprof = 3
+    for _ in range(nprof):
+        flush_l2()
+        frame()
+    fgl.sync()
+    kern = fgl.timings()
+    fgl.enable_timing(False)
+    fgl.reset_timings()
+    for k in kern:
+        k["ms_per_frame"] = k["ms_total"] / nprof
+    kern.sort(key=lambda k: -k["ms_total"])
+    peak, peak_src = measured_peaks()
+    top = next((k for k in kern if k["algorithmic_bytes"] > 0), kern[0])
+    t_launch = top["ms_total"] / top["launches"] / 1e3
+    bytes_launch = top["algorithmic_bytes"] / top["launches"]
+    achieved = bytes_launch / t_launch / 1e9
+    roofline = {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
+                "avg_launch_ms": t_launch * 1e3, "share_of_frame": top["ms_per_frame"] / max(1e-9, sum(k["ms_per_frame"] for k in kern))}
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            factor = cpu_factor(args.workload)
+            times, cw, ch = time_reference(args.workload, 1, factor)
+            cpu = {"value": cw * ch / 1e6 / times[0], "unit": "Mpixels/s", "cores": 1, "kind": "reference",
+                   "sample": "%s at %dx%d (1/%d linear resolution), 1 frame of oracle/_ref/ref_driver, single thread (the reference has no threads)"
+                             % (scene_file, cw, ch, factor), "ms_per_frame": 1e3 * times[0]}
+        line = {"metric": "mpixels_per_s", "value": out_px / 1e6 / (ms / 1e3), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "reference assets (obj/*), camera/light of the scene file",
+                "config": {"workload": desc, "triangles": sc.triangles, "width": W, "height": H,
+                           "l2": "explicit 256 MiB flush between timed frames" if flush_buf is not None else "planes (%.0f MB) exceed the 126 MB L2" % (plane_bytes / 1e6)},
+                "frames_per_s": 1e3 / ms,
+                "e2e": {"value": out_px / 1e6 / (e2e_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(h2d_bytes(sc)), "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "kernels": [{"name": k["name"], "ms_per_frame": round(k["ms_per_frame"], 4), "launches_per_frame": k["launches"] / nprof,
+                             "gbps": (k["algorithmic_bytes"] / max(1e-12, k["ms_total"] / 1e3) / 1e9) if k["algorithmic_bytes"] else None}
+                            for k in kern]}
+        print(json.dumps(line))
+    sc.free()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def h2d_bytes(sc):
+    # per frame the facade uploads one DrawCmd record per mesh per raster pass (shadow + geometry/forward)
+    return 0 if sc is None else 2 * 512 * 8
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.impl == "reference":
+        if args.steps > 3:
+            args.steps = 3  # each reference frame is seconds of CPU time; keep the arm within minutes
+        args.warmup = min(args.warmup, 1)
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
