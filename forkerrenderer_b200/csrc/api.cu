@@ -131,7 +131,7 @@ void fill_light_consts(fgl_ctx* c, LightPass& L)
     L.biasSlope = c->params.shadow_bias_slope, L.biasMin = c->params.shadow_bias_min;
     L.shadowIntensity = c->params.shadow_intensity, L.areaLight = c->params.area_light_size;
     L.pcfFilter = c->params.pcf_filter_size, L.pcssFilter = c->params.pcss_blocker_filter_size;
-    L.disk = nullptr, L.chunkOf = nullptr, L.useAO = 1;
+    L.disk = nullptr, L.chunkOf = nullptr, L.vis = nullptr, L.useAO = 1;
     L.writeF32 = c->params.materialize_frame_f32;
 }
 

@@ -71,6 +71,7 @@ struct LightPass
     uint8_t* rgb8;
     const float2* disk;        // accepted unit-disk samples of the replayed stream (lighting phase)
     const unsigned* chunkOf;   // PCSS: per pixel index of its first 32-sample chunk; NULL = PCF (2 * pixel)
+    const float* vis;          // PCF / PCSS: visibility per pixel, computed by the warp-per-pixel filter kernels (stream.cu)
 };
 
 // ---- host-side objects -----------------------------------------------------------------------------------
@@ -158,6 +159,7 @@ struct fgl_ctx
     std::vector<TimingRec> timings;
     std::vector<cudaEvent_t> eventPool;
     uint64_t               launches = 0;
+    int                    lastUncertain = 0;  // PCSS: uncertain pixels of the last chain (diagnostics)
 };
 
 // error helpers ------------------------------------------------------------------------------------------------

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
         p.param.x *= ao[v];
         V3    lightDir = vnormalize(vsub(lp, p.pos)), viewDir = vnormalize(vsub(eye, p.pos));
         float visibility = 0.f;
-        if (L.shadowOn)
+        if (L.vis) visibility = L.vis[base + v];  // PCF / PCSS: filtered by the warp-per-pixel kernels of stream.cu
+        else if (L.shadowOn)
         {   // shadow.cpp:109-132 with HardShadow (shadow.cpp:38-45)
             V3    sc = vadd(vscale(p.lndc, 0.5f), v3(0.5f, 0.5f, 0.5f));
             float bias = fmaxf(L.biasSlope * (1.f - vdot(p.nrm, lightDir)), L.biasMin);
@@ -143,76 +144,6 @@ __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
     {
         L.rgb8[base * 3] = q8[0], L.rgb8[base * 3 + 1] = q8[1], L.rgb8[base * 3 + 2] = q8[2];
     }
-}
-
-// ---- lighting, one warp per pixel (PCF / PCSS): lane = tap of the replayed sample stream ---------------------------
-// shadow.cpp:47-63.  `first` = index of the first of the 64 accepted disk samples this filter consumes.
-__device__ __forceinline__ float pcf_warp(const LightPass& L, V3 sc, float bias, float filterSize, size_t first, int lane)
-{
-    int cnt = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-    {
-        float2 d = __ldg(L.disk + first + h * 32 + lane);
-        float  u = sc.x + d.x * filterSize, v = sc.y + d.y * filterSize;
-        float  sampleDepth = shadow_lookup(L.sm, u, v);
-        cnt += __popc(__ballot_sync(0xffffffffu, sc.z <= sampleDepth + bias));
-    }
-    return (float)cnt * (1.f / 64.f);  // 64 additions of 1/64 are exact: the sum is count / 64
-}
-
-// shadow.cpp:65-90 over the 32 samples starting at `first`; returns dBlocker (0 when no tap blocks)
-__device__ __forceinline__ float blocker_warp(const LightPass& L, V3 sc, float bias, size_t first, int lane)
-{
-    float2   d = __ldg(L.disk + first + lane);
-    float    ox = (float)((double)d.x * L.pcssFilter), oy = (float)((double)d.y * L.pcssFilter);
-    float    sampleDepth = shadow_lookup(L.sm, sc.x + ox, sc.y + oy);
-    unsigned mask = __ballot_sync(0xffffffffu, sc.z > sampleDepth + bias);
-    if (mask == 0) return 0.f;
-    float sum = 0.f;
-    float n = 0.f;
-    for (unsigned m = mask; m; m &= m - 1)
-    {   // ordered sum over the blocking taps, in tap order
-        int b = __ffs(m) - 1;
-        sum += __shfl_sync(0xffffffffu, sampleDepth, b);
-        n += 1.f;
-    }
-    return sum / n;
-}
-
-__global__ void __launch_bounds__(256) k_lighting_warp(LightPass L)
-{
-    const size_t n = (size_t)L.W * L.H;
-    const int    lane = threadIdx.x & 31;
-    size_t       idx = (size_t)L.row0 * L.W + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (idx >= (size_t)L.row1 * L.W) return;
-    PixelIn p = load_pixel(L, n, idx);
-    V3      eye = v3(L.eye[0], L.eye[1], L.eye[2]), lp = v3(L.lightPos[0], L.lightPos[1], L.lightPos[2]);
-    V3      lightDir = vnormalize(vsub(lp, p.pos)), viewDir = vnormalize(vsub(eye, p.pos));
-    V3      sc = vadd(vscale(p.lndc, 0.5f), v3(0.5f, 0.5f, 0.5f));
-    float   bias = fmaxf(L.biasSlope * (1.f - vdot(p.nrm, lightDir)), L.biasMin);
-    float   visibility;
-    if (L.shadowMode == FGL_SHADOW_PCF) visibility = pcf_warp(L, sc, bias, (float)L.pcfFilter, idx * 64, lane);
-    else
-    {   // shadow.cpp:92-106
-        size_t first = (size_t)L.chunkOf[idx] * 32;
-        float  dBlocker = blocker_warp(L, sc, bias, first, lane);
-        if ((double)dBlocker < 0.001) visibility = 1.f;
-        else
-        {
-            float penumbra = (sc.z - dBlocker) * L.areaLight / dBlocker;
-            float filterSize = (float)(L.pcfFilter * (double)penumbra);
-            visibility = pcf_warp(L, sc, bias, filterSize, first + 32, lane);
-        }
-    }
-    if (lane != 0) return;
-    V3 col = shade_pixel(L, p, visibility, lightDir, viewDir);
-    if (L.writeF32)
-    {
-        float* f = L.planes.p[FGL_PLANE_FRAME];
-        f[idx] = col.x, f[n + idx] = col.y, f[2 * n + idx] = col.z;
-    }
-    L.rgb8[idx * 3] = quant8(col.x), L.rgb8[idx * 3 + 1] = quant8(col.y), L.rgb8[idx * 3 + 2] = quant8(col.z);
 }
 
 // ---- quantise / SSAA ---------------------------------------------------------------------------------------------
@@ -418,17 +349,11 @@ int fgl_run_lighting(fgl_ctx* c, const LightPass& L)
 {
     size_t   nPix = (size_t)L.W * (L.row1 - L.row0);
     uint64_t bytes = nPix * (80 + 3 + (L.writeF32 ? 12 : 0));
-    if (!L.shadowOn || L.shadowMode == FGL_SHADOW_HARD)
     {
-        LaunchScope ls(c, "lighting_hard", bytes);
+        LaunchScope ls(c, "lighting", bytes + (L.vis ? nPix * 4 : 0));
         bool        vec = (((size_t)L.W * L.H) % 4 == 0) && (((size_t)L.row0 * L.W) % 4 == 0) && (nPix % 4 == 0);
         if (vec) k_lighting_hard<4><<<(unsigned)((nPix / 4 + 127) / 128), 128, 0, c->stream>>>(L);
         else k_lighting_hard<1><<<(unsigned)((nPix + 127) / 128), 128, 0, c->stream>>>(L);
-    }
-    else
-    {
-        LaunchScope ls(c, L.shadowMode == FGL_SHADOW_PCF ? "lighting_pcf" : "lighting_pcss", bytes + nPix * 4);
-        k_lighting_warp<<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(L);
     }
     return check_launch(c, "lighting");
 }

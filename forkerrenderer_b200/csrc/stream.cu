@@ -145,29 +145,50 @@ __global__ void k_acc_add(unsigned long long* acc, const int* total) { *acc += (
 // ---- PCSS chain ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fix_depth(float d) { return ((double)d < 0.001) ? 1.f : d; }  // shadow.cpp:33-34
 
-// separable box min / max of the fixed-up shadow map, radius r
-__global__ void k_minmax_h(const float* sm, int W, int H, int r, float* omin, float* omax)
+// separable box min / max of the fixed-up shadow map over the window [x + lo, x + hi] x [y + lo, y + hi]
+// (lo = -r, hi = r: centred box of the search footprint; lo = 0, hi = bw - 1: box anchored at its first texel)
+__global__ void k_minmax_h(const float* sm, int W, int H, int lo, int hi, float* omin, float* omax)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     float mn = __int_as_float(0x7f800000), mx = -mn;
-    for (int i = max(0, x - r); i <= min(W - 1, x + r); ++i)
+    for (int i = max(0, x + lo); i <= min(W - 1, x + hi); ++i)
     {
         float d = fix_depth(__ldg(sm + (size_t)y * W + i));
         mn = fminf(mn, d), mx = fmaxf(mx, d);
     }
     omin[(size_t)y * W + x] = mn, omax[(size_t)y * W + x] = mx;
 }
-__global__ void k_minmax_v(const float* imin, const float* imax, int W, int H, int r, float* omin, float* omax)
+__global__ void k_minmax_v(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     float mn = __int_as_float(0x7f800000), mx = -mn;
-    for (int j = max(0, y - r); j <= min(H - 1, y + r); ++j)
+    for (int j = max(0, y + lo); j <= min(H - 1, y + hi); ++j)
     {
         mn = fminf(mn, __ldg(imin + (size_t)j * W + x)), mx = fmaxf(mx, __ldg(imax + (size_t)j * W + x));
     }
     omin[(size_t)y * W + x] = mn, omax[(size_t)y * W + x] = mx;
+}
+
+// ---- chunk signatures ------------------------------------------------------------------------------------------------
+// The unit square [-1,1)^2 of the disk samples is cut into 8 x 8 cells at the exact thresholds -1 + k/4.
+// sig[c] has bit (8 ky + kx) set iff chunk c (32 consecutive accepted disk samples) has a sample in cell (kx, ky).
+// A constant of the stream, like the sample table itself.
+__device__ __forceinline__ int cell_of(float x)
+{
+    return (x >= -0.75f) + (x >= -0.5f) + (x >= -0.25f) + (x >= 0.f) + (x >= 0.25f) + (x >= 0.5f) + (x >= 0.75f);
+}
+__global__ void __launch_bounds__(256) k_signatures(const float2* disk, size_t nChunks, unsigned long long* sig)
+{
+    size_t chunk = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int    lane = threadIdx.x & 31;
+    if (chunk >= nChunks) return;
+    float2   d = __ldg(disk + chunk * 32 + lane);
+    int      bit = cell_of(d.y) * 8 + cell_of(d.x);
+    unsigned lo = __reduce_or_sync(0xffffffffu, bit < 32 ? 1u << bit : 0u);
+    unsigned hi = __reduce_or_sync(0xffffffffu, bit >= 32 ? 1u << (bit - 32) : 0u);
+    if (lane == 0) sig[chunk] = (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
 
 struct ChainPass
@@ -234,9 +255,63 @@ __device__ __forceinline__ bool blocker_any(const ShadowMapD& sm, const float2* 
     return __any_sync(0xffffffffu, s.z > sampleDepth + s.w);
 }
 
+// Per uncertain pixel: F = cells whose every tap certainly blocks, E = cells in which a tap can block at all.
+// A chunk with a sample in an F cell has a blocker; a chunk with no sample in any E cell has none; only the rest
+// needs its 32 taps evaluated.  Cell (kx, ky) covers sample coordinates [-1 + kx/4, -1 + (kx+1)/4]: the tap
+// coordinate u = sc.x + float(x * fs) and its texel index are monotone in x, so the cell maps into the texel rectangle
+// spanned by its two threshold columns / rows; box min / max maps anchored at the rectangle's first texel (a
+// superset of the rectangle) give conservative answers.  One warp per pixel, two cells per lane.
+struct MaskPass
+{
+    ShadowMapD   sm;
+    const float *boxMin, *boxMax;
+    int          bw;
+    double       fs;
+};
+__global__ void __launch_bounds__(256) k_pixel_masks(MaskPass P, int nU, const float4* Usc, unsigned long long* UF, unsigned long long* UE)
+{
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= nU) return;
+    float4   s = Usc[j];
+    unsigned fbits[2], ebits[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+        int   cell = lane + 32 * h, kx = cell & 7, ky = cell >> 3;
+        float tx0 = -1.f + 0.25f * (float)kx, tx1 = -1.f + 0.25f * (float)(kx + 1);
+        float ty0 = -1.f + 0.25f * (float)ky, ty1 = -1.f + 0.25f * (float)(ky + 1);
+        float u0 = s.x + (float)((double)tx0 * P.fs), u1 = s.x + (float)((double)tx1 * P.fs);
+        float v0 = s.y + (float)((double)ty0 * P.fs), v1 = s.y + (float)((double)ty1 * P.fs);
+        bool  none = u1 < 0.f || u0 > 1.f || v1 < 0.f || v0 > 1.f || !(u0 == u0) || !(v0 == v0);
+        bool  full = u0 >= 0.f && u1 <= 1.f && v0 >= 0.f && v1 <= 1.f;
+        bool  F = false, E = false;
+        if (!none)
+        {
+            int x0 = f2i_x86((float)P.sm.iw * fmaxf(u0, 0.f)), x1 = f2i_x86((float)P.sm.iw * fminf(u1, 1.f));
+            int y0 = f2i_x86((float)P.sm.ih * fmaxf(v0, 0.f)), y1 = f2i_x86((float)P.sm.ih * fminf(v1, 1.f));
+            if (x1 - x0 + 1 > P.bw || y1 - y0 + 1 > P.bw || x0 < 0 || y0 < 0 || x0 >= P.sm.w || y0 >= P.sm.h) E = true;  // cannot bound: ambiguous
+            else
+            {
+                float dmin = __ldg(P.boxMin + (size_t)y0 * P.sm.w + x0), dmax = __ldg(P.boxMax + (size_t)y0 * P.sm.w + x0);
+                E = s.z > dmin + s.w;
+                F = full && (s.z > dmax + s.w);
+            }
+        }
+        fbits[h] = __ballot_sync(0xffffffffu, F), ebits[h] = __ballot_sync(0xffffffffu, E);
+    }
+    if (lane == 0)
+    {
+        UF[j] = (unsigned long long)fbits[0] | ((unsigned long long)fbits[1] << 32);
+        UE[j] = (unsigned long long)ebits[0] | ((unsigned long long)ebits[1] << 32);
+    }
+}
+
 // Super-chunk [j0, j0 + kT) of the uncertain list: bit d of row t = blocker flag of pixel j0 + t if d of the t
-// uncertain pixels before it in this super-chunk have blockers.  One warp per 32-bit word.
+// uncertain pixels before it in this super-chunk have blockers.  One warp per 32-bit word, one lane per candidate:
+// signatures settle most candidates, the warp then evaluates the ambiguous ones tap by tap.
+// bits layout: [word][row] (rows contiguous) so that the walk kernel reads it coalesced.
 __global__ void __launch_bounds__(256) k_chain_eval(int j0, int nU, const unsigned* mState, const unsigned* Upix, const unsigned* Uc1, const float4* Usc,
+                                                    const unsigned long long* UF, const unsigned long long* UE, const unsigned long long* sig,
                                                     ShadowMapD sm, const float2* disk, double fs, uint32_t* bits)
 {
     int lane = threadIdx.x & 31;
@@ -252,15 +327,39 @@ __global__ void __launch_bounds__(256) k_chain_eval(int j0, int nU, const unsign
     size_t   p = Upix[j];
     size_t   kbase = (size_t)Uc1[j] + m0 + 32 * word;
     float4   s = Usc[j];
-    int      dmax = min(31, t - 32 * word);
-    uint32_t w = 0;
-#pragma unroll 4
-    for (int d = 0; d <= dmax; ++d)
-    {
-        bool f = blocker_any(sm, disk, fs, s, p + 2 * (kbase + d), lane);
-        w |= (f ? 1u : 0u) << d;
+    int      d = 32 * word + lane;
+    bool     valid = d <= t;
+    unsigned long long sg = valid ? __ldg(sig + p + 2 * (kbase + lane)) : 0ull;
+    unsigned long long F = UF[j], E = UE[j];
+    bool     one = (sg & F) != 0ull;
+    uint32_t w = __ballot_sync(0xffffffffu, valid && one);
+    uint32_t amb = __ballot_sync(0xffffffffu, valid && !one && (sg & E) != 0ull);
+    while (amb)
+    {   // four ambiguous candidates per round: their sample loads and shadow-map gathers are independent
+        int  b[4];
+        bool v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            v[q] = amb != 0;
+            b[q] = v[q] ? __ffs(amb) - 1 : 0;
+            amb &= amb - 1;
+        }
+        float2 d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = v[q] ? __ldg(disk + (p + 2 * (kbase + b[q])) * 32 + lane) : make_float2(0.f, 0.f);
+        float sd[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            float ox = (float)((double)d[q].x * fs), oy = (float)((double)d[q].y * fs);
+            sd[q] = v[q] ? shadow_lookup(sm, s.x + ox, s.y + oy) : __int_as_float(0x7f800000);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (__any_sync(0xffffffffu, s.z > sd[q] + s.w)) w |= 1u << b[q];
     }
-    if (lane == 0) bits[t * kTW + word] = w;
+    if (lane == 0) bits[word * kT + t] = w;
 }
 
 // One CTA: finds the pixels of the super-chunk whose flag depends on the offset, walks them serially from shared
@@ -269,53 +368,62 @@ __global__ void __launch_bounds__(kT) k_chain_walk(int j0, int nU, unsigned* mSt
 {
     typedef cub::BlockScan<int, kT> Scan;
     __shared__ typename Scan::TempStorage tmp;
-    __shared__ int      cpre[kT];      // constants (insensitive pixels with a blocker) before row t
+    __shared__ int      baseS[kT];     // per sensitive row: insensitive pixels with a blocker before it
     __shared__ short    sens[kT];      // compacted rows that depend on the offset
-    __shared__ uint8_t  flag[kT];
+    __shared__ uint8_t  flag[kT], flagS[kT];
     __shared__ int      nSens, total;
-    extern __shared__ uint32_t rows[];  // nSens x kTW words
+    extern __shared__ uint32_t rows[];  // nSens x (kTW + 1) words (odd stride: no bank conflicts on the copy)
 
-    int  t = threadIdx.x, j = j0 + t;
-    bool live = j < nU;
-    int  isConst = 1, val = 0;
+    int      t = threadIdx.x, j = j0 + t;
+    bool     live = j < nU;
+    int      words = t / 32 + 1;
+    uint32_t r[kTW];
+#pragma unroll
+    for (int w = 0; w < kTW; ++w) r[w] = (live && w < words) ? __ldg(bits + w * kT + t) : 0u;
+    int isConst = 1, val = 0;
     if (live)
     {
-        int      words = t / 32 + 1;
         uint32_t lastMask = (t % 32 == 31) ? 0xffffffffu : ((1u << (t % 32 + 1)) - 1u);
         bool     all0 = true, all1 = true;
-        for (int w = 0; w < words; ++w)
-        {
-            uint32_t b = bits[t * kTW + w], m = (w == words - 1) ? lastMask : 0xffffffffu;
-            all0 &= (b & m) == 0, all1 &= (b & m) == m;
-        }
+#pragma unroll
+        for (int w = 0; w < kTW; ++w)
+            if (w < words)
+            {
+                uint32_t m = (w == words - 1) ? lastMask : 0xffffffffu;
+                all0 &= (r[w] & m) == 0, all1 &= (r[w] & m) == m;
+            }
         isConst = all0 || all1, val = all1 ? 1 : 0;
     }
     int cp, sp;
     Scan(tmp).ExclusiveSum(isConst ? val : 0, cp);
     __syncthreads();
     Scan(tmp).ExclusiveSum(isConst ? 0 : 1, sp);
-    cpre[t] = cp;
     flag[t] = (uint8_t)val;
     if (!isConst)
     {
         sens[sp] = (short)t;
-        for (int w = 0; w < kTW; ++w) rows[sp * kTW + w] = w <= t / 32 ? bits[t * kTW + w] : 0u;
+        baseS[sp] = cp;
+#pragma unroll
+        for (int w = 0; w < kTW; ++w) rows[sp * (kTW + 1) + w] = r[w];
     }
     if (t == kT - 1) nSens = sp + (isConst ? 0 : 1), total = cp + (isConst ? val : 0);
     __syncthreads();
     if (t == 0)
     {
         int ms = 0;  // sensitive pixels with a blocker so far
-        for (int i = 0; i < nSens; ++i)
-        {
-            int      row = sens[i];
-            int      d = cpre[row] + ms;
-            uint32_t b = (rows[i * kTW + (d >> 5)] >> (d & 31)) & 1u;
-            flag[row] = (uint8_t)b;
+        int n = nSens;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i)
+        {   // the only serial dependency: ms -> word address -> bit -> ms
+            int      d = baseS[i] + ms;
+            uint32_t b = (rows[i * (kTW + 1) + (d >> 5)] >> (d & 31)) & 1u;
+            flagS[i] = (uint8_t)b;
             ms += (int)b;
         }
         *mState += (unsigned)(total + ms);
     }
+    __syncthreads();
+    if (t < nSens) flag[sens[t]] = flagS[t];
     __syncthreads();
     if (live) flagU[j] = flag[t];
 }
@@ -326,11 +434,75 @@ __global__ void __launch_bounds__(256) k_pixel_flags(size_t n, const int* isU, c
     if (idx >= n) return;
     hasBlocker[idx] = isU[idx] ? (int)flagU[posU[idx]] : isC1[idx];
 }
-__global__ void __launch_bounds__(256) k_chunk_index(size_t n, const int* kpre, unsigned* chunkOf)
+// chunk index of every pixel, visibility 1 for the pixels without a blocker (shadow.cpp:96-99), list of the others
+__global__ void __launch_bounds__(256) k_chunk_index(size_t n, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis, unsigned* blockerList,
+                                                     unsigned* nBlockers)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     chunkOf[idx] = (unsigned)idx + 2u * (unsigned)kpre[idx];
+    vis[idx] = 1.f;
+    if (hasB[idx]) blockerList[kpre[idx]] = (unsigned)idx;
+    if (idx == n - 1) *nBlockers = (unsigned)(kpre[idx] + hasB[idx]);
+}
+
+// shadow.cpp:47-63 for one pixel by one warp: 64 taps, two per lane; the sum of 1/64 steps is exact
+__device__ __forceinline__ float pcf_taps(const ShadowMapD& sm, float4 s, float filterSize, float2 d1, float2 d2)
+{
+    float a = shadow_lookup(sm, s.x + d1.x * filterSize, s.y + d1.y * filterSize);
+    float b = shadow_lookup(sm, s.x + d2.x * filterSize, s.y + d2.y * filterSize);
+    int   cnt = __popc(__ballot_sync(0xffffffffu, s.z <= a + s.w)) + __popc(__ballot_sync(0xffffffffu, s.z <= b + s.w));
+    return (float)cnt * (1.f / 64.f);
+}
+
+// PCSS visibility of the pixels that have a blocker (shadow.cpp:92-106): persistent warps over the blocker list.
+__global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
+                                                        ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
+{
+    const int      lane = threadIdx.x & 31;
+    const unsigned nb = *nBlockers, nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nWarps)
+    {
+        unsigned idx = blockerList[i];
+        float4   s = sc4[idx];
+        size_t   first = (size_t)chunkOf[idx] * 32;
+        float2   d0 = __ldg(disk + first + lane), d1 = __ldg(disk + first + 32 + lane), d2 = __ldg(disk + first + 64 + lane);
+        float    ox = (float)((double)d0.x * fs), oy = (float)((double)d0.y * fs);
+        float    sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
+        unsigned mask = __ballot_sync(0xffffffffu, s.z > sampleDepth + s.w);
+        float    sum = 0.f, n = 0.f;
+        for (unsigned m = mask; m; m &= m - 1)
+        {   // ordered sum over the blocking taps (shadow.cpp:78-84)
+            sum += __shfl_sync(0xffffffffu, sampleDepth, __ffs(m) - 1);
+            n += 1.f;
+        }
+        float dBlocker = mask ? sum / n : 0.f;
+        float v = 1.f;
+        if (!((double)dBlocker < 0.001))
+        {
+            float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
+            v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
+        }
+        if (lane == 0) vis[idx] = v;
+    }
+}
+
+// PCF visibility of every pixel of the band (shadow.cpp:47-63, 120-124): one warp per pixel
+__global__ void __launch_bounds__(256) k_pcf_visibility(ChainPass P, int row0, int row1, const float2* disk, float filterSize, float* vis)
+{
+    size_t n = (size_t)P.W * P.H;
+    int    lane = threadIdx.x & 31;
+    size_t idx = (size_t)row0 * P.W + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (idx >= (size_t)row1 * P.W) return;
+    V3     pos = v3(P.worldpos[idx], P.worldpos[n + idx], P.worldpos[2 * n + idx]);
+    V3     nrm = v3(P.normal[idx], P.normal[n + idx], P.normal[2 * n + idx]);
+    V3     ln = v3(P.lndc[idx], P.lndc[n + idx], P.lndc[2 * n + idx]);
+    V3     lightDir = vnormalize(vsub(v3(P.lightPos[0], P.lightPos[1], P.lightPos[2]), pos));
+    V3     sc = vadd(vscale(ln, 0.5f), v3(0.5f, 0.5f, 0.5f));
+    float  bias = fmaxf(P.biasSlope * (1.f - vdot(nrm, lightDir)), P.biasMin);
+    float2 d1 = __ldg(disk + idx * 64 + lane), d2 = __ldg(disk + idx * 64 + 32 + lane);
+    float  v = pcf_taps(P.sm, make_float4(sc.x, sc.y, sc.z, bias), filterSize, d1, d2);
+    if (lane == 0) vis[idx] = v;
 }
 }  // namespace
 
@@ -348,7 +520,9 @@ struct SampleStream
     bool               ssaoThisFrame = false;
     unsigned long long ssaoSamples = 0;
     // chain scratch
-    DevBuf smTmpMin, smTmpMax, smMin, smMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, bits, flagU, hasB, kpre, chunkOf, mState;
+    DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
+    DevBuf sig, vis, blockerList;
+    unsigned long long sigChunks = 0;
 };
 
 static SampleStream* S_of(fgl_ctx* c)
@@ -362,7 +536,7 @@ void fgl_stream_destroy(fgl_ctx* c)
     SampleStream* s = c->stream_state;
     if (!s) return;
     DevBuf* all[] = { &s->ckpt, &s->window, &s->tileCounts, &s->tileOffsets, &s->counters, &s->ball, &s->disk, &s->smTmpMin, &s->smTmpMax, &s->smMin,
-                      &s->smMax, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
+                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
                       &s->chunkOf, &s->mState };
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
@@ -486,27 +660,51 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
 {
     SampleStream*      s = S_of(c);
     size_t             n = (size_t)L.W * L.H;
+    cudaStream_t       st = c->stream;
     unsigned long long rawBegin = s->ssaoThisFrame ? s->ballRawEnd : 0ull;
     // PCF: 64 samples per pixel; PCSS: chunk index <= 3 n, plus the 96 samples of the last pixel
-    unsigned long long need = L.shadowMode == FGL_SHADOW_PCF ? (unsigned long long)n * 64 : ((unsigned long long)n * 3 + 4) * 32;
+    bool               pcss = L.shadowMode == FGL_SHADOW_PCSS;
+    unsigned long long nChunks = pcss ? (unsigned long long)n * 3 + 4 : (unsigned long long)n * 2;
+    unsigned long long need = nChunks * 32;
     if (s->diskRawBegin != rawBegin || s->diskNeed < need)
     {
-        s->diskNeed = 0;
+        s->diskNeed = 0, s->sigChunks = 0;
         if (int rc = build_table<2>(c, s, s->disk, rawBegin, need, nullptr)) return rc;
         s->diskNeed = need, s->diskRawBegin = rawBegin;
     }
+    if (pcss && s->sigChunks < nChunks)
+    {
+        if (int rc = fgl_reserve(c, s->sig, (size_t)nChunks * 8)) return rc;
+        LaunchScope ls(c, "stream_signatures", nChunks * 264);
+        k_signatures<<<(unsigned)((nChunks * 32 + 255) / 256), 256, 0, st>>>((const float2*)s->disk.p, (size_t)nChunks, (unsigned long long*)s->sig.p);
+        s->sigChunks = nChunks;
+    }
     L.disk = (const float2*)s->disk.p;
     L.chunkOf = nullptr;
-    if (L.shadowMode == FGL_SHADOW_PCF) return FGL_OK;
+    if (int rc = fgl_reserve(c, s->vis, n * 4)) return rc;
+    L.vis = (const float*)s->vis.p;
+
+    ChainPass P;
+    P.W = L.W, P.H = L.H;
+    P.worldpos = L.planes.p[FGL_PLANE_WORLDPOS], P.normal = L.planes.p[FGL_PLANE_NORMAL], P.lndc = L.planes.p[FGL_PLANE_LIGHTNDC];
+    memcpy(P.lightPos, L.lightPos, 12);
+    P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
+    P.smMin = P.smMax = nullptr, P.r = 0, P.fsF = 0.f;
+    if (!pcss)
+    {
+        size_t      nPix = (size_t)L.W * (L.row1 - L.row0);
+        LaunchScope ls(c, "pcf_visibility", nPix * (36 + 512 + 4));
+        k_pcf_visibility<<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, st>>>(P, L.row0, L.row1, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
+        return FGL_OK;
+    }
 
     // ---- PCSS chain --------------------------------------------------------------------------------------------
-    cudaStream_t st = c->stream;
-    size_t       smN = (size_t)L.sm.w * L.sm.h;
-    DevBuf*      f4[] = { &s->smTmpMin, &s->smTmpMax, &s->smMin, &s->smMax };
+    size_t  smN = (size_t)L.sm.w * L.sm.h;
+    DevBuf* f4[] = { &s->smTmpMin, &s->smTmpMax, &s->smMin, &s->smMax, &s->boxMin, &s->boxMax };
     for (DevBuf* b : f4)
         if (int rc = fgl_reserve(c, *b, smN * 4)) return rc;
     if (int rc = fgl_reserve(c, s->sc4, n * 16)) return rc;
-    DevBuf* i4[] = { &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->hasB, &s->kpre };
+    DevBuf* i4[] = { &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->hasB, &s->kpre, &s->blockerList };
     for (DevBuf* b : i4)
         if (int rc = fgl_reserve(c, *b, (n + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->chunkOf, n * 4)) return rc;
@@ -516,18 +714,16 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     float fsF = (float)L.pcssFilter;
     if (!((double)fsF >= L.pcssFilter)) fsF = nextafterf(fsF, 1e30f);  // |(float)(d * fs)| <= fsF for |d| < 1
     int r = (int)ceil((double)L.sm.iw * (double)fsF) + 1;
+    int bw = (int)ceil(0.25 * (double)L.sm.iw * (double)fsF) + 2;
     {
-        LaunchScope ls(c, "pcss_minmax", smN * 24);
+        LaunchScope ls(c, "pcss_minmax", smN * 48);
         dim3        grid((L.sm.w + 127) / 128, L.sm.h);
-        k_minmax_h<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, r, (float*)s->smTmpMin.p, (float*)s->smTmpMax.p);
-        ++c->launches;
-        k_minmax_v<<<grid, 128, 0, st>>>((const float*)s->smTmpMin.p, (const float*)s->smTmpMax.p, L.sm.w, L.sm.h, r, (float*)s->smMin.p, (float*)s->smMax.p);
+        k_minmax_h<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, -r, r, (float*)s->smTmpMin.p, (float*)s->smTmpMax.p);
+        k_minmax_v<<<grid, 128, 0, st>>>((const float*)s->smTmpMin.p, (const float*)s->smTmpMax.p, L.sm.w, L.sm.h, -r, r, (float*)s->smMin.p, (float*)s->smMax.p);
+        k_minmax_h<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, 0, bw - 1, (float*)s->smTmpMin.p, (float*)s->smTmpMax.p);
+        k_minmax_v<<<grid, 128, 0, st>>>((const float*)s->smTmpMin.p, (const float*)s->smTmpMax.p, L.sm.w, L.sm.h, 0, bw - 1, (float*)s->boxMin.p, (float*)s->boxMax.p);
+        c->launches += 3;
     }
-    ChainPass P;
-    P.W = L.W, P.H = L.H;
-    P.worldpos = L.planes.p[FGL_PLANE_WORLDPOS], P.normal = L.planes.p[FGL_PLANE_NORMAL], P.lndc = L.planes.p[FGL_PLANE_LIGHTNDC];
-    memcpy(P.lightPos, L.lightPos, 12);
-    P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
     P.smMin = (const float*)s->smMin.p, P.smMax = (const float*)s->smMax.p, P.r = r, P.fsF = fsF;
     unsigned nb = (unsigned)((n + 255) / 256);
     {
@@ -543,7 +739,10 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     if (int rc = fgl_reserve(c, s->Upix, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Uc1, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Usc, (size_t)(nU + 1) * 16)) return rc;
+    if (int rc = fgl_reserve(c, s->UF, (size_t)(nU + 1) * 8)) return rc;
+    if (int rc = fgl_reserve(c, s->UE, (size_t)(nU + 1) * 8)) return rc;
     if (int rc = fgl_reserve(c, s->flagU, (size_t)nU + 16)) return rc;
+    c->lastUncertain = nU;
     if (nU > 0)
     {
         {
@@ -551,25 +750,34 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
             k_gather_uncertain<<<nb, 256, 0, st>>>(n, (const int*)s->isU.p, (const int*)s->posU.p, (const int*)s->c1pre.p, (const float4*)s->sc4.p,
                                                    (unsigned*)s->Upix.p, (unsigned*)s->Uc1.p, (float4*)s->Usc.p);
         }
+        {
+            MaskPass M;
+            M.sm = L.sm, M.boxMin = (const float*)s->boxMin.p, M.boxMax = (const float*)s->boxMax.p, M.bw = bw, M.fs = L.pcssFilter;
+            LaunchScope ls(c, "pcss_masks", (uint64_t)nU * (16 + 16 + 512));
+            k_pixel_masks<<<(unsigned)(((size_t)nU * 32 + 255) / 256), 256, 0, st>>>(M, nU, (const float4*)s->Usc.p, (unsigned long long*)s->UF.p,
+                                                                                    (unsigned long long*)s->UE.p);
+        }
         FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 16, st));
+        static bool attr = false;
+        if (!attr)
+        {
+            FGL_CUDA(c, cudaFuncSetAttribute(k_chain_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * (kTW + 1) * 4));
+            attr = true;
+        }
         const int evalWarps = 16 * kTW * (kTW + 1);
         for (int j0 = 0; j0 < nU; j0 += kT)
         {
             {
                 LaunchScope ls(c, "pcss_chain_eval", 0);
                 k_chain_eval<<<(evalWarps * 32 + 255) / 256, 256, 0, st>>>(j0, nU, (const unsigned*)s->mState.p, (const unsigned*)s->Upix.p,
-                                                                           (const unsigned*)s->Uc1.p, (const float4*)s->Usc.p, L.sm, L.disk, L.pcssFilter,
+                                                                           (const unsigned*)s->Uc1.p, (const float4*)s->Usc.p,
+                                                                           (const unsigned long long*)s->UF.p, (const unsigned long long*)s->UE.p,
+                                                                           (const unsigned long long*)s->sig.p, L.sm, L.disk, L.pcssFilter,
                                                                            (uint32_t*)s->bits.p);
             }
             {
-                static bool attr = false;
-                if (!attr)
-                {
-                    FGL_CUDA(c, cudaFuncSetAttribute(k_chain_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * kTW * 4));
-                    attr = true;
-                }
                 LaunchScope ls(c, "pcss_chain_walk", 0);
-                k_chain_walk<<<1, kT, (size_t)kT * kTW * 4, st>>>(j0, nU, (unsigned*)s->mState.p, (const uint32_t*)s->bits.p, (uint8_t*)s->flagU.p);
+                k_chain_walk<<<1, kT, (size_t)kT * (kTW + 1) * 4, st>>>(j0, nU, (unsigned*)s->mState.p, (const uint32_t*)s->bits.p, (uint8_t*)s->flagU.p);
             }
         }
     }
@@ -579,8 +787,14 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     }
     if (int rc = scan_ints(c, (const int*)s->hasB.p, (int*)s->kpre.p, n)) return rc;
     {
-        LaunchScope ls(c, "pcss_chunk_index", n * 8);
-        k_chunk_index<<<nb, 256, 0, st>>>(n, (const int*)s->kpre.p, (unsigned*)s->chunkOf.p);
+        LaunchScope ls(c, "pcss_chunk_index", n * 20);
+        k_chunk_index<<<nb, 256, 0, st>>>(n, (const int*)s->kpre.p, (const int*)s->hasB.p, (unsigned*)s->chunkOf.p, (float*)s->vis.p,
+                                          (unsigned*)s->blockerList.p, (unsigned*)s->mState.p + 2);
+    }
+    {
+        LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
+        k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + 2, (const float4*)s->sc4.p,
+                                                   (const unsigned*)s->chunkOf.p, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, (float*)s->vis.p);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
     cudaError_t e = cudaGetLastError();
