@@ -667,6 +667,7 @@ int fgl_plane_info(fgl_ctx* c, int plane, int* w, int* h, int* ch, int* bpc)
 {
     ENTER(c);
     if (plane < 0 || plane >= FGL_PLANE_COUNT || !w || !h || !ch || !bpc) return fgl_fail(c, FGL_ERR_INVALID, "fgl_plane_info: bad arguments");
+    if (int rc = flush(c)) return rc;  // pending draws define the size of the winner-id planes
     if (plane <= FGL_PLANE_AO) *w = c->planes[plane].w, *h = c->planes[plane].h, *ch = is1ch(plane) ? 1 : 3, *bpc = 4;
     else if (plane == FGL_PLANE_FRAME_RGB8) *w = c->planes[FGL_PLANE_FRAME].w, *h = c->planes[FGL_PLANE_FRAME].h, *ch = 3, *bpc = 1;
     else if (plane == FGL_PLANE_SSAA_RGB8) *w = c->ssaaW, *h = c->ssaaH, *ch = 3, *bpc = 1;

@@ -1,0 +1,51 @@
+"""Pins the CPU oracle (oracle/oracle.cpp behind the product's own host facade) to the UNMODIFIED reference: the
+sha256 fingerprints in tests/golden/reference_hashes.json were produced by oracle/_ref/ref_driver (the reference's
+own sources, compiled by oracle/Makefile).  Every plane must match bit for bit — including the 8-bit images, i.e. the
+whole mt19937 sample stream is replayed exactly."""
+import os
+
+import numpy as np
+import pytest
+
+import parity as P
+from conftest import sha
+
+FAST = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c2_pcf", "c4_hard", "c4_catbox_linear", "pbr_hard"]
+SLOW = ["c3_pcss_ssao"]
+
+
+def check(cfg, oracle_host, golden):
+    got = P.render_host(oracle_host, cfg)
+    want = golden[cfg]["planes"]
+    bad = []
+    for name, fp in want.items():
+        if name not in got:
+            bad.append(name + " (missing)")
+            continue
+        a = got[name]
+        assert list(a.shape) == fp["shape"], (name, a.shape, fp["shape"])
+        if sha(a) != fp["sha256"]:
+            bad.append(name)
+    assert not bad, "oracle differs from the reference on %s: %s" % (cfg, bad)
+
+
+@pytest.mark.parametrize("cfg", FAST)
+def test_oracle_matches_reference(cfg, oracle_host, golden):
+    check(cfg, oracle_host, golden)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("cfg", SLOW)
+def test_oracle_matches_reference_4k(cfg, oracle_host, golden):
+    if not os.environ.get("FGL_SLOW"):
+        pytest.skip("about two minutes of CPU; set FGL_SLOW=1")
+    check(cfg, oracle_host, golden)
+
+
+def test_golden_was_generated_by_the_reference_when_it_is_here(golden):
+    """If the reference binary is present, re-run it on C1 and compare with the committed fingerprints."""
+    if not P.have_ref():
+        pytest.skip("oracle/_ref/ref_driver not built")
+    ref = P.run_reference("c1_hard")
+    for name in ("depth", "frame_u8", "ids_camera", "normal"):
+        assert sha(ref[name]) == golden["c1_hard"]["planes"][name]["sha256"], name
