@@ -159,7 +159,7 @@ struct fgl_ctx
     std::vector<TimingRec> timings;
     std::vector<cudaEvent_t> eventPool;
     uint64_t               launches = 0;
-    int                    lastUncertain = 0;  // PCSS: uncertain pixels of the last chain (diagnostics)
+    int                    lastUncertain = 0, lastChainIters = 0;  // PCSS: uncertain pixels / super-chunks of the last chain (diagnostics)
 };
 
 // error helpers ------------------------------------------------------------------------------------------------

@@ -30,8 +30,8 @@ namespace
 constexpr int    kMT = 624;
 constexpr int    kCB = 256;                      // generator blocks per checkpoint
 constexpr size_t kWindowCand = (size_t)64 << 20;  // candidates per build window
-constexpr int    kT = 1024;                      // uncertain pixels per super-chunk of the PCSS chain
-constexpr int    kTW = kT / 32;
+constexpr int    kT = 2048;                      // uncertain pixels per super-chunk of the PCSS chain
+constexpr int    kWin = 64;                      // candidate offsets evaluated per row, centred on the prediction
 
 __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
 {
@@ -306,36 +306,38 @@ __global__ void __launch_bounds__(256) k_pixel_masks(MaskPass P, int nU, const f
     }
 }
 
-// Super-chunk [j0, j0 + kT) of the uncertain list: bit d of row t = blocker flag of pixel j0 + t if d of the t
-// uncertain pixels before it in this super-chunk have blockers.  One warp per 32-bit word, one lane per candidate:
-// signatures settle most candidates, the warp then evaluates the ambiguous ones tap by tap.
-// bits layout: [word][row] (rows contiguous) so that the walk kernel reads it coalesced.
-__global__ void __launch_bounds__(256) k_chain_eval(int j0, int nU, const unsigned* mState, const unsigned* Upix, const unsigned* Uc1, const float4* Usc,
-                                                    const unsigned long long* UF, const unsigned long long* UE, const unsigned long long* sig,
-                                                    ShadowMapD sm, const float2* disk, double fs, uint32_t* bits)
+// ---- the chain proper --------------------------------------------------------------------------------------------
+// Row j of the uncertain list (pixel p_j, c1_j certain blockers before it) uses chunk p_j + 2 (c1_j + m_j), where
+// m_j = number of uncertain rows before j that have a blocker.  m_j is only known once all earlier rows are, but
+// its value can be predicted well: blocker flags evaluated at ANY nearby offset are draws from the same
+// distribution, so the prefix sums of a "pilot" evaluation (every row at a crude offset, fully parallel) track the
+// true m_j to within a random-walk drift.  Rows are then processed in super-chunks of up to kT rows from an exactly
+// known state (j0, m0): each row is evaluated for the kWin candidates around its predicted offset (parallel), a
+// single thread walks the rows whose flag depends on the candidate, and the first row whose true offset falls
+// outside its window ends the super-chunk there (the next one restarts from that row with exact state), so the
+// result never depends on the prediction — only the speed does.
+struct ChainRows
 {
-    int lane = threadIdx.x & 31;
-    int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (task >= 16 * kTW * (kTW + 1)) return;
-    int g = 0;
-    while (16 * (g + 1) * (g + 2) <= task) ++g;  // rows 32g .. 32g+31 have g + 1 words each
-    int rem = task - 16 * g * (g + 1);
-    int t = 32 * g + rem / (g + 1), word = rem % (g + 1);
-    int j = j0 + t;
-    if (j >= nU) return;
-    unsigned m0 = *mState;
-    size_t   p = Upix[j];
-    size_t   kbase = (size_t)Uc1[j] + m0 + 32 * word;
-    float4   s = Usc[j];
-    int      d = 32 * word + lane;
-    bool     valid = d <= t;
-    unsigned long long sg = valid ? __ldg(sig + p + 2 * (kbase + lane)) : 0ull;
-    unsigned long long F = UF[j], E = UE[j];
-    bool     one = (sg & F) != 0ull;
-    uint32_t w = __ballot_sync(0xffffffffu, valid && one);
-    uint32_t amb = __ballot_sync(0xffffffffu, valid && !one && (sg & E) != 0ull);
+    int                       nU;
+    const unsigned *          Upix, *Uc1;
+    const float4*             Usc;
+    const unsigned long long *UF, *UE, *sig;
+    ShadowMapD                sm;
+    const float2*             disk;
+    double                    fs;
+};
+
+// flags of up to 32 (row, chunk) pairs, one per lane: signature tests first, then the warp evaluates the ambiguous
+// pairs tap by tap (four at a time: their sample loads and shadow-map gathers are independent).  Returns the ballot.
+__device__ __forceinline__ uint32_t eval_pairs(const ChainRows& R, bool valid, int j, size_t chunk, int lane)
+{
+    unsigned long long sg = valid ? __ldg(R.sig + chunk) : 0ull;
+    unsigned long long F = valid ? __ldg(R.UF + j) : 0ull, E = valid ? __ldg(R.UE + j) : 0ull;
+    bool               one = (sg & F) != 0ull;
+    uint32_t           w = __ballot_sync(0xffffffffu, valid && one);
+    uint32_t           amb = __ballot_sync(0xffffffffu, valid && !one && (sg & E) != 0ull);
     while (amb)
-    {   // four ambiguous candidates per round: their sample loads and shadow-map gathers are independent
+    {
         int  b[4];
         bool v[4];
 #pragma unroll
@@ -345,87 +347,194 @@ __global__ void __launch_bounds__(256) k_chain_eval(int j0, int nU, const unsign
             b[q] = v[q] ? __ffs(amb) - 1 : 0;
             amb &= amb - 1;
         }
+        float4 s[4];
         float2 d[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = v[q] ? __ldg(disk + (p + 2 * (kbase + b[q])) * 32 + lane) : make_float2(0.f, 0.f);
+        for (int q = 0; q < 4; ++q)
+        {
+            int    jq = __shfl_sync(0xffffffffu, j, b[q]);
+            size_t cq = __shfl_sync(0xffffffffu, chunk, b[q]);
+            s[q] = v[q] ? __ldg(R.Usc + jq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            d[q] = v[q] ? __ldg(R.disk + cq * 32 + lane) : make_float2(0.f, 0.f);
+        }
         float sd[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
         {
-            float ox = (float)((double)d[q].x * fs), oy = (float)((double)d[q].y * fs);
-            sd[q] = v[q] ? shadow_lookup(sm, s.x + ox, s.y + oy) : __int_as_float(0x7f800000);
+            float ox = (float)((double)d[q].x * R.fs), oy = (float)((double)d[q].y * R.fs);
+            sd[q] = v[q] ? shadow_lookup(R.sm, s[q].x + ox, s[q].y + oy) : __int_as_float(0x7f800000);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (__any_sync(0xffffffffu, s.z > sd[q] + s.w)) w |= 1u << b[q];
+            if (__any_sync(0xffffffffu, s[q].z > sd[q] + s[q].w)) w |= 1u << b[q];
     }
-    if (lane == 0) bits[word * kT + t] = w;
+    return w;
 }
 
-// One CTA: finds the pixels of the super-chunk whose flag depends on the offset, walks them serially from shared
-// memory, writes every pixel's flag and advances the chain state.
-__global__ void __launch_bounds__(kT) k_chain_walk(int j0, int nU, unsigned* mState, const uint32_t* bits, uint8_t* flagU)
+// pilot: every uncertain row at the crude offset "half of the uncertain rows before it have a blocker"
+__global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot)
 {
-    typedef cub::BlockScan<int, kT> Scan;
-    __shared__ typename Scan::TempStorage tmp;
-    __shared__ int      baseS[kT];     // per sensitive row: insensitive pixels with a blocker before it
-    __shared__ short    sens[kT];      // compacted rows that depend on the offset
-    __shared__ uint8_t  flag[kT], flagS[kT];
-    __shared__ int      nSens, total;
-    extern __shared__ uint32_t rows[];  // nSens x (kTW + 1) words (odd stride: no bank conflicts on the copy)
+    int  lane = threadIdx.x & 31;
+    int  j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = j < R.nU;
+    size_t chunk = valid ? (size_t)R.Upix[j] + 2 * ((size_t)R.Uc1[j] + (size_t)(j >> 1)) : 0;
+    uint32_t w = eval_pairs(R, valid, j, chunk, lane);
+    if (valid) pilot[j] = (w >> lane) & 1u;
+}
 
-    int      t = threadIdx.x, j = j0 + t;
-    bool     live = j < nU;
-    int      words = t / 32 + 1;
-    uint32_t r[kTW];
-#pragma unroll
-    for (int w = 0; w < kTW; ++w) r[w] = (live && w < words) ? __ldg(bits + w * kT + t) : 0u;
-    int isConst = 1, val = 0;
-    if (live)
+enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_NBLOCKERS = 8 };
+
+// one warp per (row t of the super-chunk, half of its window): lane = candidate
+__global__ void __launch_bounds__(256) k_chain_eval(ChainRows R, const unsigned* state, const int* Ppre, uint32_t* win, int* winLo)
+{
+    if (state[CH_DONE]) return;
+    int lane = threadIdx.x & 31;
+    int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int t = task >> 1, half = task & 1;
+    int j0 = (int)state[CH_J0], j = j0 + t;
+    if (t >= kT || j >= R.nU) return;
+    unsigned m0 = state[CH_M0];
+    int      dhat = __ldg(Ppre + j) - __ldg(Ppre + j0);
+    int      lo = max(0, dhat - kWin / 2);
+    int      d = lo + 32 * half + lane;
+    bool     valid = d <= t;
+    size_t   chunk = (size_t)R.Upix[j] + 2 * ((size_t)R.Uc1[j] + m0 + (size_t)d);
+    uint32_t w = eval_pairs(R, valid, j, chunk, lane);
+    if (lane == 0)
     {
-        uint32_t lastMask = (t % 32 == 31) ? 0xffffffffu : ((1u << (t % 32 + 1)) - 1u);
-        bool     all0 = true, all1 = true;
-#pragma unroll
-        for (int w = 0; w < kTW; ++w)
-            if (w < words)
-            {
-                uint32_t m = (w == words - 1) ? lastMask : 0xffffffffu;
-                all0 &= (r[w] & m) == 0, all1 &= (r[w] & m) == m;
-            }
-        isConst = all0 || all1, val = all1 ? 1 : 0;
+        win[t * 2 + half] = w;
+        if (half == 0) winLo[t] = lo;
     }
-    int cp, sp;
-    Scan(tmp).ExclusiveSum(isConst ? val : 0, cp);
-    __syncthreads();
-    Scan(tmp).ExclusiveSum(isConst ? 0 : 1, sp);
-    flag[t] = (uint8_t)val;
-    if (!isConst)
+}
+
+// One CTA, two rows per thread: finds the rows whose flag depends on the candidate, walks them serially, validates
+// that every row's true offset was inside its window, commits the valid prefix and advances the state.
+__device__ __forceinline__ void classify_row(unsigned long long bits, int first, int last, int& isConst, int& val)
+{   // flag constant over candidate indices [first, last] of the window?  (empty range: treated as dependent)
+    if (first > last)
     {
-        sens[sp] = (short)t;
-        baseS[sp] = cp;
-#pragma unroll
-        for (int w = 0; w < kTW; ++w) rows[sp * (kTW + 1) + w] = r[w];
+        isConst = 0, val = 0;
+        return;
     }
-    if (t == kT - 1) nSens = sp + (isConst ? 0 : 1), total = cp + (isConst ? val : 0);
-    __syncthreads();
-    if (t == 0)
+    int                n = last - first + 1;
+    unsigned long long m = (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << first;
+    bool               all0 = (bits & m) == 0ull, all1 = (bits & m) == m;
+    isConst = all0 || all1, val = all1 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kT / 2) k_chain_walk(int nU, unsigned* state, const uint32_t* win, const int* winLo, uint8_t* flagU)
+{
+    typedef cub::BlockScan<unsigned long long, kT / 2> Scan64;
+    typedef cub::BlockScan<int, kT / 2>                Scan32;
+    __shared__ union
     {
-        int ms = 0;  // sensitive pixels with a blocker so far
-        int n = nSens;
+        typename Scan64::TempStorage a;
+        typename Scan32::TempStorage b;
+    } tmp;
+    __shared__ unsigned long long bitsS[kT];
+    __shared__ int                offS[kT];  // per candidate-dependent row: constant blockers before it minus its window origin
+    __shared__ short              sensRow[kT];
+    __shared__ short              idxS[kT];
+    __shared__ uint8_t            nvS[kT], flagS[kT];
+    __shared__ int                nSens, tstop, firstBad;
+
+    if (state[CH_DONE]) return;
+    const int j0 = (int)state[CH_J0];
+    const int nLive = min(kT, nU - j0);
+    if (threadIdx.x == 0) firstBad = kT, tstop = kT;
+    unsigned long long bits[2];
+    int                lo[2], nv[2], isConst[2], val[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        int t = threadIdx.x * 2 + k;
+        isConst[k] = 1, val[k] = 0, lo[k] = 0, nv[k] = 1, bits[k] = 0ull;
+        if (t < nLive)
+        {
+            bits[k] = (unsigned long long)win[t * 2] | ((unsigned long long)win[t * 2 + 1] << 32);
+            lo[k] = winLo[t];
+            nv[k] = min(kWin, t - lo[k] + 1);
+            classify_row(bits[k], 0, nv[k] - 1, isConst[k], val[k]);
+        }
+    }
+    // one scan for both prefix counts: low word = rows with a constant blocker, high word = candidate-dependent rows.
+    // Second round: a row's true offset lies in [cp, cp + sp], so its flag only has to be constant over that part of
+    // its window; fewer dependent rows means a shorter serial walk.
+    unsigned long long item[2], pre[2], aggregate;
+    int                cp[2], sp[2];
+    for (int round = 0; round < 2; ++round)
+    {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) item[k] = (unsigned long long)(isConst[k] ? val[k] : 0) | ((unsigned long long)(isConst[k] ? 0 : 1) << 32);
+        Scan64(tmp.a).ExclusiveSum(item, pre, aggregate);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            cp[k] = (int)(pre[k] & 0xffffffffu), sp[k] = (int)(pre[k] >> 32);
+            int t = threadIdx.x * 2 + k;
+            if (round == 0 && t < nLive && !isConst[k])
+                classify_row(bits[k], max(0, cp[k] - lo[k]), min(nv[k] - 1, cp[k] + sp[k] - lo[k]), isConst[k], val[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (!isConst[k])
+        {
+            int i = sp[k];
+            sensRow[i] = (short)(threadIdx.x * 2 + k), offS[i] = cp[k] - lo[k], bitsS[i] = bits[k], nvS[i] = (uint8_t)nv[k];
+        }
+    if (threadIdx.x == 0) nSens = (int)(aggregate >> 32);
+    __syncthreads();
+    const int n = nSens;
+    if (threadIdx.x == 0)
+    {
+        int ms = 0;
 #pragma unroll 4
         for (int i = 0; i < n; ++i)
-        {   // the only serial dependency: ms -> word address -> bit -> ms
-            int      d = baseS[i] + ms;
-            uint32_t b = (rows[i * (kTW + 1) + (d >> 5)] >> (d & 31)) & 1u;
+        {   // the only serial dependency of the whole pass: ms -> bit index -> bit -> ms (range check deferred)
+            int idx = offS[i] + ms;
+            int b = (int)((bitsS[i] >> (idx & 63)) & 1ull);
+            idxS[i] = (short)idx;
             flagS[i] = (uint8_t)b;
-            ms += (int)b;
+            ms += b;
         }
-        *mState += (unsigned)(total + ms);
     }
     __syncthreads();
-    if (t < nSens) flag[sens[t]] = flagS[t];
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (idxS[i] < 0 || idxS[i] >= (short)nvS[i]) atomicMin(&tstop, (int)sensRow[i]);  // first row whose offset left its window
     __syncthreads();
-    if (live) flagU[j] = flag[t];
+    // blockers among the candidate-dependent rows before each row, then validation of the constant rows
+    int sb[2], msb[2], msTotal;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) sb[k] = (!isConst[k] && (threadIdx.x * 2 + k) < tstop) ? (int)flagS[sp[k]] : 0;
+    Scan32(tmp.b).ExclusiveSum(sb, msb, msTotal);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        int t = threadIdx.x * 2 + k;
+        if (t < nLive && t < tstop && isConst[k])
+        {
+            int idx = cp[k] + msb[k] - lo[k];
+            if (idx < 0 || idx >= nv[k]) atomicMin(&firstBad, t);
+        }
+    }
+    __syncthreads();
+    const int valid = min(min(tstop, firstBad), nLive);  // >= 1: row 0 always sits at offset 0 of its window
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        int t = threadIdx.x * 2 + k;
+        if (t < valid) flagU[j0 + t] = isConst[k] ? (uint8_t)val[k] : flagS[sp[k]];
+        if (t == valid) state[CH_M0] += (unsigned)(cp[k] + msb[k]);  // blockers among the committed rows
+    }
+    if (threadIdx.x == 0)
+    {
+        if (valid == kT) state[CH_M0] += (unsigned)((int)(aggregate & 0xffffffffu) + msTotal);
+        state[CH_J0] = (unsigned)(j0 + valid);
+        state[CH_ITERS] += 1;
+        if (j0 + valid >= nU) state[CH_DONE] = 1;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_pixel_flags(size_t n, const int* isU, const int* isC1, const int* posU, const uint8_t* flagU, int* hasBlocker)
@@ -521,7 +630,7 @@ struct SampleStream
     unsigned long long ssaoSamples = 0;
     // chain scratch
     DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
-    DevBuf sig, vis, blockerList;
+    DevBuf sig, vis, blockerList, pilot, Ppre, winLo;
     unsigned long long sigChunks = 0;
 };
 
@@ -536,7 +645,7 @@ void fgl_stream_destroy(fgl_ctx* c)
     SampleStream* s = c->stream_state;
     if (!s) return;
     DevBuf* all[] = { &s->ckpt, &s->window, &s->tileCounts, &s->tileOffsets, &s->counters, &s->ball, &s->disk, &s->smTmpMin, &s->smTmpMax, &s->smMin,
-                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
+                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->pilot, &s->Ppre, &s->winLo, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
                       &s->chunkOf, &s->mState };
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
@@ -708,8 +817,7 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     for (DevBuf* b : i4)
         if (int rc = fgl_reserve(c, *b, (n + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->chunkOf, n * 4)) return rc;
-    if (int rc = fgl_reserve(c, s->mState, 16)) return rc;
-    if (int rc = fgl_reserve(c, s->bits, (size_t)kT * kTW * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->mState, 64)) return rc;
 
     float fsF = (float)L.pcssFilter;
     if (!((double)fsF >= L.pcssFilter)) fsF = nextafterf(fsF, 1e30f);  // |(float)(d * fs)| <= fsF for |d| < 1
@@ -757,28 +865,44 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
             k_pixel_masks<<<(unsigned)(((size_t)nU * 32 + 255) / 256), 256, 0, st>>>(M, nU, (const float4*)s->Usc.p, (unsigned long long*)s->UF.p,
                                                                                     (unsigned long long*)s->UE.p);
         }
-        FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 16, st));
-        static bool attr = false;
-        if (!attr)
+        FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 64, st));
+        ChainRows R;
+        R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
+        R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p, R.sig = (const unsigned long long*)s->sig.p;
+        R.sm = L.sm, R.disk = L.disk, R.fs = L.pcssFilter;
+        if (int rc = fgl_reserve(c, s->pilot, (size_t)(nU + 1) * 4)) return rc;
+        if (int rc = fgl_reserve(c, s->Ppre, (size_t)(nU + 1) * 4)) return rc;
+        if (int rc = fgl_reserve(c, s->bits, (size_t)kT * 2 * 4)) return rc;
+        if (int rc = fgl_reserve(c, s->winLo, (size_t)kT * 4)) return rc;
         {
-            FGL_CUDA(c, cudaFuncSetAttribute(k_chain_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kT * (kTW + 1) * 4));
-            attr = true;
+            LaunchScope ls(c, "pcss_chain_pilot", (uint64_t)nU * 48);
+            k_chain_pilot<<<(nU + 255) / 256, 256, 0, st>>>(R, (int*)s->pilot.p);
         }
-        const int evalWarps = 16 * kTW * (kTW + 1);
-        for (int j0 = 0; j0 < nU; j0 += kT)
+        FGL_CUDA(c, cudaMemsetAsync((int*)s->pilot.p + nU, 0, 4, st));
+        if (int rc = scan_ints(c, (const int*)s->pilot.p, (int*)s->Ppre.p, (size_t)nU + 1)) return rc;
+        int launched = 0;
+        for (;;)
         {
+            int batch = launched == 0 ? (nU + kT - 1) / kT + (nU + kT - 1) / kT / 4 + 2 : 8;
+            for (int it = 0; it < batch; ++it)
             {
-                LaunchScope ls(c, "pcss_chain_eval", 0);
-                k_chain_eval<<<(evalWarps * 32 + 255) / 256, 256, 0, st>>>(j0, nU, (const unsigned*)s->mState.p, (const unsigned*)s->Upix.p,
-                                                                           (const unsigned*)s->Uc1.p, (const float4*)s->Usc.p,
-                                                                           (const unsigned long long*)s->UF.p, (const unsigned long long*)s->UE.p,
-                                                                           (const unsigned long long*)s->sig.p, L.sm, L.disk, L.pcssFilter,
-                                                                           (uint32_t*)s->bits.p);
+                {
+                    LaunchScope ls(c, "pcss_chain_eval", 0);
+                    k_chain_eval<<<(kT * 2 * 32 + 255) / 256, 256, 0, st>>>(R, (const unsigned*)s->mState.p, (const int*)s->Ppre.p, (uint32_t*)s->bits.p,
+                                                                          (int*)s->winLo.p);
+                }
+                {
+                    LaunchScope ls(c, "pcss_chain_walk", 0);
+                    k_chain_walk<<<1, kT / 2, 0, st>>>(nU, (unsigned*)s->mState.p, (const uint32_t*)s->bits.p, (const int*)s->winLo.p, (uint8_t*)s->flagU.p);
+                }
             }
-            {
-                LaunchScope ls(c, "pcss_chain_walk", 0);
-                k_chain_walk<<<1, kT, (size_t)kT * (kTW + 1) * 4, st>>>(j0, nU, (unsigned*)s->mState.p, (const uint32_t*)s->bits.p, (uint8_t*)s->flagU.p);
-            }
+            launched += batch;
+            unsigned hs[4];
+            FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 16, cudaMemcpyDeviceToHost, st));
+            FGL_CUDA(c, cudaStreamSynchronize(st));
+            c->lastChainIters = (int)hs[CH_ITERS];
+            if (hs[CH_DONE]) break;
+            if (launched > 4 * ((nU + kT - 1) / kT) + 4096) return fgl_fail(c, FGL_ERR_STATE, "PCSS chain did not converge");
         }
     }
     {
@@ -789,11 +913,11 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     {
         LaunchScope ls(c, "pcss_chunk_index", n * 20);
         k_chunk_index<<<nb, 256, 0, st>>>(n, (const int*)s->kpre.p, (const int*)s->hasB.p, (unsigned*)s->chunkOf.p, (float*)s->vis.p,
-                                          (unsigned*)s->blockerList.p, (unsigned*)s->mState.p + 2);
+                                          (unsigned*)s->blockerList.p, (unsigned*)s->mState.p + CH_NBLOCKERS);
     }
     {
         LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
-        k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + 2, (const float4*)s->sc4.p,
+        k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, (const float4*)s->sc4.p,
                                                    (const unsigned*)s->chunkOf.p, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, (float*)s->vis.p);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
