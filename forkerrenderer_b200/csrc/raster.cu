@@ -11,6 +11,7 @@
 //   k_resolve_*      one thread per pixel: decode the winner, redo its barycentrics, run the fragment program
 //                    (depthshader.h:30-36, gshader.h:95-201, phongshader.h:90-169, pbrshader.h:90-180) and write the
 //                    SoA planes; pixels without a winner receive the planes' clear values (fused clear).
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "fgl_internal.h"
@@ -56,7 +57,7 @@ __device__ __forceinline__ SetupRegs load_setup(const TriSetup* s, int prim)
 }
 
 // -------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin)
+__global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int smallArea)
 {
     int prim = primBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (prim >= P.nPrims) return;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin)
     int bw = xmax - xmin + 1, bh = ymax - ymin + 1, nb = 0;
     if (!(flags & TRI_SKIP))
     {
-        if (bw * bh <= kSmallArea) flags |= TRI_SMALL;
+        if (bw * bh <= smallArea) flags |= TRI_SMALL;
         else
         {
             flags |= TRI_LARGE;
@@ -160,6 +161,44 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin)
         float4* vo = reinterpret_cast<float4*>(P.vary + prim);
 #pragma unroll
         for (int i = 0; i < 12; ++i) vo[i] = make_float4(vy.f[4 * i], vy.f[4 * i + 1], vy.f[4 * i + 2], vy.f[4 * i + 3]);
+    }
+}
+
+// Exclusive scan of up to a few hundred thousand ints by one CTA (the two-kernel device-wide scan costs more in
+// launch latency than the work is worth for the meshes of the reference's scenes).
+struct ScanCarry
+{
+    int running;
+    __device__ int operator()(int blockAggregate)
+    {
+        int old = running;
+        running += blockAggregate;
+        return old;
+    }
+};
+__global__ void __launch_bounds__(1024) k_scan_small(const int* in, int* out, int n)
+{
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    ScanCarry carry;
+    carry.running = 0;
+    for (int base = 0; base < n; base += 4096)
+    {
+        int v[4], r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            int i = base + threadIdx.x * 4 + k;
+            v[k] = i < n ? in[i] : 0;
+        }
+        Scan(tmp).ExclusiveSum(v, r, carry);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            int i = base + threadIdx.x * 4 + k;
+            if (i < n) out[i] = r[k];
+        }
     }
 }
 
@@ -187,6 +226,7 @@ __device__ __forceinline__ EdgeInt make_edges(const SetupRegs& s, int px, int py
     return e;
 }
 
+template <bool PRECHECK>
 __device__ __forceinline__ void depth_test_pixel(const RasterPass& P, const TriCover& tc, const SetupRegs& s, int prim, int px, int py)
 {
     V3 bary;
@@ -195,7 +235,8 @@ __device__ __forceinline__ void depth_test_pixel(const RasterPass& P, const TriC
     if (!(z < 3.402823466e+38f)) return;                // never below the FLT_MAX clear value (forkergl.cpp:189)
     unsigned long long  key = ((unsigned long long)depth_to_ordered(z) << 32) | (unsigned)prim;
     unsigned long long* cell = P.vis + (size_t)px + (size_t)py * P.W;
-    if (key < *((volatile unsigned long long*)cell)) atomicMin(cell, key);
+    // the pre-read saves atomics under overdraw but serialises a load in front of each one
+    if (!PRECHECK || key < *((volatile unsigned long long*)cell)) atomicMin(cell, key);
 }
 
 __global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegin)
@@ -213,7 +254,7 @@ __global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegi
         long long c0 = e.e0, c1 = e.e1, c2 = e.e2;
         for (int py = s.ymin; py <= s.ymax; ++py)
         {
-            if (!sane || (c0 | c1 | c2) >= 0) depth_test_pixel(P, tc, s, prim, px, py);
+            if (!sane || (c0 | c1 | c2) >= 0) depth_test_pixel<true>(P, tc, s, prim, px, py);
             c0 += e.dy0, c1 += e.dy1, c2 += e.dy2;
         }
         e.e0 += e.dx0, e.e1 += e.dx1, e.e2 += e.dx2;
@@ -254,7 +295,7 @@ __global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBeg
         EdgeInt e = make_edges(s, px, y0);
         for (int py = y0; py <= y1; ++py)
         {
-            if (!sane || (e.e0 | e.e1 | e.e2) >= 0) depth_test_pixel(P, tc, s, cachedTri, px, py);
+            if (!sane || (e.e0 | e.e1 | e.e2) >= 0) depth_test_pixel<false>(P, tc, s, cachedTri, px, py);
             e.e0 += e.dy0, e.e1 += e.dy1, e.e2 += e.dy2;
         }
     }
@@ -474,21 +515,31 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
     int          primBegin = c->flushedPrims;
     int          nNew = P.nPrims - primBegin;
     size_t       nPix = (size_t)P.W * P.H;
+    // Thread-per-triangle only pays off when there are enough small triangles to fill the machine; otherwise every
+    // triangle takes the warp-per-block path (a small triangle is a single block).
+    const int smallArea = nNew >= 65536 ? kSmallArea : 0;
     if (nNew > 0)
     {
         {
             LaunchScope ls(c, "setup", (uint64_t)nNew * 320);
-            k_setup<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin);
+            k_setup<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin, smallArea);
         }
         // exclusive scan of the block counts of the new triangles -> blkScan[primBegin .. nPrims]
-        size_t tmpBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
-        if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
+        if (nNew < 200000)
         {
+            LaunchScope ls(c, "scan", (uint64_t)nNew * 8);
+            k_scan_small<<<1, 1024, 0, st>>>(P.nblk + primBegin, P.blkScan, nNew + 1);
+        }
+        else
+        {
+            size_t tmpBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
+            if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
             LaunchScope ls(c, "scan", (uint64_t)nNew * 8);
             // the scan runs over nNew + 1 inputs so that entry nNew holds the total (nblk has one spare, zeroed, slot)
             cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
         }
+        if (smallArea > 0)
         {
             LaunchScope ls(c, "raster_small", 0);
             k_raster_small<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin);

@@ -2,6 +2,8 @@
 // (shadow.cpp:23-132) and the 8-bit quantise (buffer.cpp:113-126); SSAO (render.cpp:214-286); the in-place
 // Gaussian blur as the recurrence it is (buffer.cpp:59-98); the SSAA box resolve (render.cpp:291-343); clears and
 // layout conversions for the host accessors.
+#include <cstdlib>
+
 #include "fgl_internal.h"
 
 namespace
@@ -82,6 +84,11 @@ __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
                 float4 q = __ldcs(reinterpret_cast<const float4*>(src[j] + base));
                 in[j][0] = q.x, in[j][1] = q.y, in[j][2] = q.z, in[j][3] = q.w;
             }
+            else if constexpr (VEC == 2)
+            {
+                float2 q = __ldcs(reinterpret_cast<const float2*>(src[j] + base));
+                in[j][0] = q.x, in[j][1] = q.y;
+            }
             else in[j][0] = __ldcs(src[j] + base);
         }
     }
@@ -90,6 +97,11 @@ __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
     {
         float4 q = __ldcs(reinterpret_cast<const float4*>(L.planes.p[FGL_PLANE_AO] + base));
         ao[0] = q.x, ao[1] = q.y, ao[2] = q.z, ao[3] = q.w;
+    }
+    else if constexpr (VEC == 2)
+    {
+        float2 q = __ldcs(reinterpret_cast<const float2*>(L.planes.p[FGL_PLANE_AO] + base));
+        ao[0] = q.x, ao[1] = q.y;
     }
     else ao[0] = __ldcs(L.planes.p[FGL_PLANE_AO] + base);
 
@@ -128,6 +140,7 @@ __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
         {
             float* dst = L.planes.p[FGL_PLANE_FRAME] + c * n + base;
             if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(outc[c][0], outc[c][1], outc[c][2], outc[c][3]));
+            else if constexpr (VEC == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(outc[c][0], outc[c][1]));
             else *dst = outc[c][0];
         }
     }
@@ -139,6 +152,11 @@ __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
             w[i] = (uint32_t)q8[4 * i] | ((uint32_t)q8[4 * i + 1] << 8) | ((uint32_t)q8[4 * i + 2] << 16) | ((uint32_t)q8[4 * i + 3] << 24);
         uint32_t* dst = reinterpret_cast<uint32_t*>(L.rgb8 + base * 3);
         dst[0] = w[0], dst[1] = w[1], dst[2] = w[2];
+    }
+    else if constexpr (VEC == 2)
+    {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(L.rgb8 + base * 3);
+        dst[0] = (uint16_t)(q8[0] | (q8[1] << 8)), dst[1] = (uint16_t)(q8[2] | (q8[3] << 8)), dst[2] = (uint16_t)(q8[4] | (q8[5] << 8));
     }
     else
     {
@@ -352,7 +370,9 @@ int fgl_run_lighting(fgl_ctx* c, const LightPass& L)
     {
         LaunchScope ls(c, "lighting", bytes + (L.vis ? nPix * 4 : 0));
         bool        vec = (((size_t)L.W * L.H) % 4 == 0) && (((size_t)L.row0 * L.W) % 4 == 0) && (nPix % 4 == 0);
-        if (vec) k_lighting_hard<4><<<(unsigned)((nPix / 4 + 127) / 128), 128, 0, c->stream>>>(L);
+        static int  vecWidth = getenv("FGL_LIGHT_VEC") ? atoi(getenv("FGL_LIGHT_VEC")) : 2;  // 2 pixels/thread: 64-bit loads, 40 % more resident warps than 4 (profiles/)
+        if (vec && vecWidth == 4) k_lighting_hard<4><<<(unsigned)((nPix / 4 + 127) / 128), 128, 0, c->stream>>>(L);
+        else if (vec && vecWidth == 2) k_lighting_hard<2><<<(unsigned)((nPix / 2 + 127) / 128), 128, 0, c->stream>>>(L);
         else k_lighting_hard<1><<<(unsigned)((nPix + 127) / 128), 128, 0, c->stream>>>(L);
     }
     return check_launch(c, "lighting");
