@@ -224,11 +224,6 @@ int flush(fgl_ctx* c)
         if (int rc = materialize(c, FGL_PLANE_FRAME)) return rc;
         if (fullBand) c->planes[FGL_PLANE_DEPTH].fillPending = false;
         else if (int rc = materialize(c, FGL_PLANE_DEPTH)) return rc;
-        if (c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD)
-        {
-            c->flushedPrims = c->primCounter;
-            return fgl_fail(c, FGL_ERR_UNSUPPORTED, "forward mode with PCF/PCSS needs per-fragment stream ordinals (not built yet); use FGL_SHADOW_HARD");
-        }
         fill_light_consts(c, L);
         if (c->shadowOn)
         {
@@ -246,10 +241,20 @@ int flush(fgl_ctx* c)
         c->flushedPrims = c->primCounter;
         return FGL_OK;
     }
-    int rc = fgl_run_raster(c, P, planes_dev(c), nullptr, &L);
+    bool stochasticForward = c->pass == FGL_PASS_FORWARD && c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD;
+    int  rc = fgl_run_raster(c, P, planes_dev(c), nullptr, stochasticForward ? nullptr : &L);
     c->flushedPrims = c->primCounter;
     c->frameRgb8Valid = false;
-    return rc;
+    if (rc || !stochasticForward) return rc;
+    // Forward + PCF / PCSS: every fragment that passed the depth test when it was submitted consumed samples, so the
+    // winners' stream positions depend on all of them.  (Exact for a pass flushed once, which is how Render::DoForwardPass
+    // submits it; a pass flushed in pieces restarts the sample stream at each flush.)
+    size_t        nSites = 0;
+    const float4* sc4 = nullptr;
+    if ((rc = fgl_run_forward_sites(c, P, L, &nSites, &sc4))) return rc;
+    if (nSites)
+        if ((rc = fgl_stream_site_visibility(c, L, nSites, sc4, 0, nSites))) return rc;
+    return fgl_run_resolve_forward(c, P, planes_dev(c), L);
 }
 
 int ensure_rgb8(fgl_ctx* c)

@@ -52,6 +52,10 @@ struct RasterPass
     int*            blkScan;  // exclusive scan of nblk, nPrims + 1 entries
     unsigned long long* vis;
     const TexD*     textures;
+    // forward mode with a stochastic shadow filter: per-pixel fragment lists and the winner's stream position
+    unsigned *          fragCount, *fragOffset;
+    unsigned long long* frags;
+    const int*          siteOfPixel;
 };
 
 struct PlanesD
@@ -148,6 +152,7 @@ struct fgl_ctx
     int                   primCounter = 0;  // submission index of the next triangle in this pass
     int                   flushedPrims = 0;
     DevBuf                drawsDev, setup, vary, zndc, nblk, blkScan, scanTmp;
+    DevBuf                fragCount, fragOffset, frags, nPass, passOff, siteOfPixel, siteKeys, siteVals, siteSc4, sortTmp;
     void*                 pinned = nullptr;
     size_t                pinnedCap = 0;
 
@@ -193,6 +198,8 @@ struct LaunchScope
 
 // kernels (raster.cu) ------------------------------------------------------------------------------------------
 int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb8, const LightPass* forwardLight);
+int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t* nSites, const float4** sc4);
+int fgl_run_resolve_forward(fgl_ctx* c, const RasterPass& P, PlanesD planes, const LightPass& L);
 // kernels (shade.cu)
 int fgl_run_fill(fgl_ctx* c, float* dst, size_t n, float value);
 int fgl_run_fill_rgb(fgl_ctx* c, float* dst, size_t nPixels, const float rgb[3]);

@@ -12,7 +12,10 @@
 //                    (depthshader.h:30-36, gshader.h:95-201, phongshader.h:90-169, pbrshader.h:90-180) and write the
 //                    SoA planes; pixels without a winner receive the planes' clear values (fused clear).
 #include <cub/block/block_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+
+#include <algorithm>
 
 #include "fgl_internal.h"
 
@@ -226,19 +229,36 @@ __device__ __forceinline__ EdgeInt make_edges(const SetupRegs& s, int px, int py
     return e;
 }
 
-template <bool PRECHECK>
+// MODE 0: depth test.  MODE 1 / 2 (forward mode with a stochastic shadow filter): count / record EVERY covered
+// fragment per pixel, because each fragment that passes the depth test at submission time consumes samples of the
+// stream (phongshader.h:139-149), not only the final winner.
+enum { RM_DEPTH = 0, RM_COUNT = 1, RM_FILL = 2 };
+template <int MODE, bool PRECHECK>
 __device__ __forceinline__ void depth_test_pixel(const RasterPass& P, const TriCover& tc, const SetupRegs& s, int prim, int px, int py)
 {
     V3 bary;
     if (!cover_test(tc, px, py, bary)) return;
     float z = vdot(bary, v3(s.d[0], s.d[1], s.d[2]));  // forkergl.cpp:180
     if (!(z < 3.402823466e+38f)) return;                // never below the FLT_MAX clear value (forkergl.cpp:189)
+    if (MODE == RM_COUNT)
+    {
+        atomicAdd(P.fragCount + (size_t)px + (size_t)py * P.W, 1u);
+        return;
+    }
+    if (MODE == RM_FILL)
+    {
+        size_t   pix = (size_t)px + (size_t)py * P.W;
+        unsigned slot = P.fragOffset[pix] + atomicAdd(P.fragCount + pix, 1u);
+        P.frags[slot] = ((unsigned long long)(unsigned)prim << 32) | __float_as_uint(z);
+        return;
+    }
     unsigned long long  key = ((unsigned long long)depth_to_ordered(z) << 32) | (unsigned)prim;
     unsigned long long* cell = P.vis + (size_t)px + (size_t)py * P.W;
     // the pre-read saves atomics under overdraw but serialises a load in front of each one
     if (!PRECHECK || key < *((volatile unsigned long long*)cell)) atomicMin(cell, key);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegin)
 {
     int prim = primBegin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,13 +274,14 @@ __global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegi
         long long c0 = e.e0, c1 = e.e1, c2 = e.e2;
         for (int py = s.ymin; py <= s.ymax; ++py)
         {
-            if (!sane || (c0 | c1 | c2) >= 0) depth_test_pixel<true>(P, tc, s, prim, px, py);
+            if (!sane || (c0 | c1 | c2) >= 0) depth_test_pixel<MODE, true>(P, tc, s, prim, px, py);
             c0 += e.dy0, c1 += e.dy1, c2 += e.dy2;
         }
         e.e0 += e.dx0, e.e1 += e.dx1, e.e2 += e.dx2;
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBegin, int nNew)
 {
     const int lane = threadIdx.x & 31;
@@ -295,7 +316,7 @@ __global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBeg
         EdgeInt e = make_edges(s, px, y0);
         for (int py = y0; py <= y1; ++py)
         {
-            if (!sane || (e.e0 | e.e1 | e.e2) >= 0) depth_test_pixel<false>(P, tc, s, cachedTri, px, py);
+            if (!sane || (e.e0 | e.e1 | e.e2) >= 0) depth_test_pixel<MODE, false>(P, tc, s, cachedTri, px, py);
             e.e0 += e.dy0, e.e1 += e.dy1, e.e2 += e.dy2;
         }
     }
@@ -475,7 +496,8 @@ __global__ void __launch_bounds__(128) k_resolve_forward(RasterPass P, PlanesD o
     V3      lightDir = vnormalize(vsub(lp, s.posWS)), viewDir = vnormalize(vsub(ep, s.posWS));
     V3      halfwayDir = vnormalize(vadd(lightDir, viewDir));
     float   visibility = 0.f;
-    if (P.shadowOn)
+    if (P.shadowOn && L.vis) visibility = L.vis[P.siteOfPixel[idx]];  // PCF / PCSS at this fragment's position in the stream
+    else if (P.shadowOn)
     {   // shadow.cpp:109-132, HardShadow branch
         V3    sc = vadd(vscale(s.lightNDC, 0.5f), v3(0.5f, 0.5f, 0.5f));
         float bias = fmaxf(L.biasSlope * (1.f - vdot(s.normal, lightDir)), L.biasMin);
@@ -505,9 +527,182 @@ __global__ void __launch_bounds__(128) k_resolve_forward(RasterPass P, PlanesD o
     }
     st3(out.p[FGL_PLANE_FRAME], n, idx, color);
 }
+
+// ---- forward mode + stochastic shadow filter: which fragments consumed samples, and in which order ------------------
+// Per pixel: sort its fragments by primitive id (= submission order), the ones that pass the depth test at
+// submission time are the running minima (strict <, forkergl.cpp:189).  Pass 1 counts them, pass 2 emits
+// key = prim << 32 | px << 16 | py (the reference scans px outer / py inner inside a triangle, forkergl.cpp:169-171),
+// value = pixel index, top bit set for the pixel's final winner.
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_frag_passing(RasterPass P, unsigned* nPass, const unsigned* passOff, unsigned long long* keys, unsigned* vals)
+{
+    size_t n = (size_t)P.W * P.H, pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= n) return;
+    unsigned            cnt = P.fragCount[pix];
+    unsigned long long* f = P.frags + P.fragOffset[pix];
+    if (!EMIT)
+    {   // insertion sort by (prim, depth bits): prim is unique per pixel
+        for (unsigned i = 1; i < cnt; ++i)
+        {
+            unsigned long long k = f[i];
+            unsigned           j = i;
+            for (; j > 0 && f[j - 1] > k; --j) f[j] = f[j - 1];
+            f[j] = k;
+        }
+    }
+    float    runMin = 3.402823466e+38f;
+    unsigned np = 0, out = EMIT ? passOff[pix] : 0;
+    int      px = (int)(pix % P.W), py = (int)(pix / P.W);
+    unsigned total = EMIT ? nPass[pix] : 0;
+    for (unsigned i = 0; i < cnt; ++i)
+    {
+        float z = __uint_as_float((unsigned)(f[i] & 0xffffffffull));
+        if (z < runMin)
+        {
+            runMin = z;
+            if (EMIT)
+            {
+                keys[out + np] = (f[i] & 0xffffffff00000000ull) | ((unsigned long long)px << 16) | (unsigned long long)py;
+                vals[out + np] = (unsigned)pix | (np + 1 == total ? 0x80000000u : 0u);
+            }
+            ++np;
+        }
+    }
+    if (!EMIT) nPass[pix] = np;
+}
+
+__global__ void __launch_bounds__(256) k_site_of_pixel(size_t nSites, const unsigned* vals, int* siteOfPixel)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSites) return;
+    unsigned v = vals[i];
+    if (v & 0x80000000u) siteOfPixel[v & 0x7fffffffu] = (int)i;
+}
+
+// shadow coordinate + bias of every stream consumer (phongshader.h:130-149 / pbrshader.h:131-150 up to the call of
+// CalculateShadowVisibility): the fragment program's surface interpolation at that fragment
+__global__ void __launch_bounds__(128) k_site_coords(RasterPass P, LightPass L, size_t nSites, const unsigned long long* keys, float4* sc4)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSites) return;
+    unsigned long long key = keys[i];
+    int                prim = (int)(key >> 32), px = (int)((key >> 16) & 0xffff), py = (int)(key & 0xffff);
+    SetupRegs          s = load_setup(P.setup, prim);
+    TriCover           tc = make_cover(s.X[0], s.Y[0], s.X[1], s.Y[1], s.X[2], s.Y[2]);
+    V3                 bary;
+    cover_test(tc, px, py, bary);
+    const DrawCmdD&    d = find_draw(P.draws, P.nDraws, prim);
+    float              vy[48];
+    load_vary(P.vary, prim, vy);
+    Surface sf = interpolate_surface(P, d, vy, bary, d.kind == FGL_SHADER_PBR ? d.mat.pbr_normal_map : d.mat.normal_map);
+    V3      lightDir = vnormalize(vsub(v3(d.lightPos[0], d.lightPos[1], d.lightPos[2]), sf.posWS));
+    V3      sc = vadd(vscale(sf.lightNDC, 0.5f), v3(0.5f, 0.5f, 0.5f));
+    float   bias = fmaxf(L.biasSlope * (1.f - vdot(sf.normal, lightDir)), L.biasMin);
+    sc4[i] = make_float4(sc.x, sc.y, sc.z, bias);
+}
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------------------
+// Forward mode with PCF / PCSS: enumerates the fragments that consumed samples, in consumption order (the "sites").
+// Outputs (owned by the context): siteOfPixel (site of each pixel's final winner, -1 = no fragment) and the sites'
+// shadow coordinates.  Re-runs the raster loops in counting / recording mode over all triangles of the pass.
+int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t* nSitesOut, const float4** sc4Out)
+{
+    cudaStream_t st = c->stream;
+    size_t       nPix = (size_t)P.W * P.H;
+    int          nPrims = P.nPrims;
+    if (int rc = fgl_reserve(c, c->fragCount, (nPix + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, c->fragOffset, (nPix + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, c->nPass, (nPix + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, c->passOff, (nPix + 1) * 4)) return rc;
+    if (int rc = fgl_reserve(c, c->siteOfPixel, nPix * 4)) return rc;
+    P.fragCount = (unsigned*)c->fragCount.p, P.fragOffset = (unsigned*)c->fragOffset.p, P.siteOfPixel = (int*)c->siteOfPixel.p;
+    // block work items over ALL triangles of the pass (the depth raster may have been flushed in pieces)
+    if (int rc = fgl_reserve(c, c->blkScan, ((size_t)nPrims + 1) * 4)) return rc;
+    P.blkScan = (int*)c->blkScan.p;
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, P.nblk, P.blkScan, nPrims + 1, st);
+    size_t tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, (unsigned*)nullptr, (unsigned*)nullptr, (int)nPix + 1, st);
+    tmpBytes = std::max(tmpBytes, tmp2);
+    if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
+    cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, P.nblk, P.blkScan, nPrims + 1, st);
+    auto raster = [&](int mode) {
+        LaunchScope ls(c, mode == RM_COUNT ? "forward_frag_count" : "forward_frag_fill", 0);
+        if (mode == RM_COUNT)
+        {
+            k_raster_small<RM_COUNT><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
+            k_raster_blocks<RM_COUNT><<<148 * 8, 256, 0, st>>>(P, 0, nPrims);
+        }
+        else
+        {
+            k_raster_small<RM_FILL><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
+            k_raster_blocks<RM_FILL><<<148 * 8, 256, 0, st>>>(P, 0, nPrims);
+        }
+        ++c->launches;
+    };
+    FGL_CUDA(c, cudaMemsetAsync(P.fragCount, 0, (nPix + 1) * 4, st));
+    raster(RM_COUNT);
+    cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, P.fragCount, P.fragOffset, (int)nPix + 1, st);
+    unsigned nFrags = 0;
+    FGL_CUDA(c, cudaMemcpyAsync(&nFrags, P.fragOffset + nPix, 4, cudaMemcpyDeviceToHost, st));
+    FGL_CUDA(c, cudaStreamSynchronize(st));
+    if (int rc = fgl_reserve(c, c->frags, ((size_t)nFrags + 1) * 8)) return rc;
+    P.frags = (unsigned long long*)c->frags.p;
+    FGL_CUDA(c, cudaMemsetAsync(P.fragCount, 0, (nPix + 1) * 4, st));
+    raster(RM_FILL);
+    unsigned nb = (unsigned)((nPix + 127) / 128);
+    {
+        LaunchScope ls(c, "forward_frag_sort", (uint64_t)nFrags * 16);
+        k_frag_passing<false><<<nb, 128, 0, st>>>(P, (unsigned*)c->nPass.p, nullptr, nullptr, nullptr);
+    }
+    FGL_CUDA(c, cudaMemsetAsync((unsigned*)c->nPass.p + nPix, 0, 4, st));
+    cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, (unsigned*)c->nPass.p, (unsigned*)c->passOff.p, (int)nPix + 1, st);
+    unsigned nSites = 0;
+    FGL_CUDA(c, cudaMemcpyAsync(&nSites, (unsigned*)c->passOff.p + nPix, 4, cudaMemcpyDeviceToHost, st));
+    FGL_CUDA(c, cudaStreamSynchronize(st));
+    if (int rc = fgl_reserve(c, c->siteKeys, ((size_t)nSites + 1) * 8 * 2)) return rc;
+    if (int rc = fgl_reserve(c, c->siteVals, ((size_t)nSites + 1) * 4 * 2)) return rc;
+    if (int rc = fgl_reserve(c, c->siteSc4, ((size_t)nSites + 1) * 16)) return rc;
+    unsigned long long *keysIn = (unsigned long long*)c->siteKeys.p, *keysOut = keysIn + nSites + 1;
+    unsigned *          valsIn = (unsigned*)c->siteVals.p, *valsOut = valsIn + nSites + 1;
+    {
+        LaunchScope ls(c, "forward_frag_emit", (uint64_t)nFrags * 8 + (uint64_t)nSites * 12);
+        k_frag_passing<true><<<nb, 128, 0, st>>>(P, (unsigned*)c->nPass.p, (const unsigned*)c->passOff.p, keysIn, valsIn);
+    }
+    FGL_CUDA(c, cudaMemsetAsync(c->siteOfPixel.p, 0xFF, nPix * 4, st));
+    if (nSites)
+    {
+        size_t sortBytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keysIn, keysOut, valsIn, valsOut, (int)nSites, 0, 64, st);
+        if (int rc = fgl_reserve(c, c->sortTmp, sortBytes)) return rc;
+        {
+            LaunchScope ls(c, "forward_site_sort", (uint64_t)nSites * 24);
+            cub::DeviceRadixSort::SortPairs(c->sortTmp.p, sortBytes, keysIn, keysOut, valsIn, valsOut, (int)nSites, 0, 64, st);
+        }
+        {
+            LaunchScope ls(c, "forward_site_coords", (uint64_t)nSites * (8 + 240 + 16));
+            k_site_of_pixel<<<(nSites + 255) / 256, 256, 0, st>>>(nSites, valsOut, (int*)c->siteOfPixel.p);
+            k_site_coords<<<(nSites + 127) / 128, 128, 0, st>>>(P, L, nSites, keysOut, (float4*)c->siteSc4.p);
+            ++c->launches;
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("forward sites: ") + cudaGetErrorString(e));
+    *nSitesOut = nSites, *sc4Out = (const float4*)c->siteSc4.p;
+    return FGL_OK;
+}
+
+int fgl_run_resolve_forward(fgl_ctx* c, const RasterPass& P, PlanesD planes, const LightPass& L)
+{
+    dim3        grid((P.W + 127) / 128, P.row1 - P.row0);
+    LaunchScope ls(c, "resolve_forward", (uint64_t)P.W * (P.row1 - P.row0) * 24);
+    k_resolve_forward<<<grid, 128, 0, c->stream>>>(P, planes, L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("resolve_forward: ") + cudaGetErrorString(e));
+    return FGL_OK;
+}
+
 int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb8, const LightPass* forwardLight)
 {
     (void)rgb8;
@@ -542,11 +737,11 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
         if (smallArea > 0)
         {
             LaunchScope ls(c, "raster_small", 0);
-            k_raster_small<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin);
+            k_raster_small<RM_DEPTH><<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin);
         }
         {
             LaunchScope ls(c, "raster_blocks", 0);
-            k_raster_blocks<<<148 * 8, 256, 0, st>>>(P, primBegin, nNew);
+            k_raster_blocks<RM_DEPTH><<<148 * 8, 256, 0, st>>>(P, primBegin, nNew);
         }
     }
     if (P.passType == FGL_PASS_SHADOW)
@@ -562,7 +757,7 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
             LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88);
             k_resolve_geometry<<<grid, 128, 0, st>>>(P, planes);
         }
-        else if (P.passType == FGL_PASS_FORWARD)
+        else if (P.passType == FGL_PASS_FORWARD && forwardLight)
         {
             LaunchScope ls(c, "resolve_forward", (uint64_t)P.W * (P.row1 - P.row0) * 24);
             k_resolve_forward<<<grid, 128, 0, st>>>(P, planes, *forwardLight);

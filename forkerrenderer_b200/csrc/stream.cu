@@ -202,11 +202,12 @@ struct ChainPass
     float        fsF;  // (float)pcss filter size: |tap offset| <= fsF
 };
 
-// per pixel: shadow coordinate + bias (shadow.cpp:109-118) and the blocker-search class
-__global__ void __launch_bounds__(256) k_classify(ChainPass P, float4* sc4, int* isU, int* isC1)
+// per pixel: shadow coordinate + bias (shadow.cpp:109-118) from the G-buffer (deferred lighting; forward mode
+// computes the same quantities per fragment in raster.cu)
+__global__ void __launch_bounds__(256) k_shadow_coords(ChainPass P, size_t first, size_t last, float4* sc4)
 {
-    size_t n = (size_t)P.W * P.H, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    size_t n = (size_t)P.W * P.H, idx = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= last) return;
     V3    pos = v3(P.worldpos[idx], P.worldpos[n + idx], P.worldpos[2 * n + idx]);
     V3    nrm = v3(P.normal[idx], P.normal[n + idx], P.normal[2 * n + idx]);
     V3    ln = v3(P.lndc[idx], P.lndc[n + idx], P.lndc[2 * n + idx]);
@@ -214,6 +215,17 @@ __global__ void __launch_bounds__(256) k_classify(ChainPass P, float4* sc4, int*
     V3    sc = vadd(vscale(ln, 0.5f), v3(0.5f, 0.5f, 0.5f));
     float bias = fmaxf(P.biasSlope * (1.f - vdot(nrm, lightDir)), P.biasMin);
     sc4[idx] = make_float4(sc.x, sc.y, sc.z, bias);
+}
+
+// blocker-search class of every site (a site = one consumer of the lighting-phase stream, in consumption order:
+// a pixel in deferred mode, a depth-test-passing fragment in forward mode)
+__global__ void __launch_bounds__(256) k_classify(ChainPass P, size_t n, const float4* sc4, int* isU, int* isC1)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float4 s4 = sc4[idx];
+    V3     sc = v3(s4.x, s4.y, s4.z);
+    float  bias = s4.w;
 
     // every tap lands at u in [ulo, uhi] (the float add is monotone in the offset, |offset| <= fsF)
     float ulo = sc.x + (-P.fsF), uhi = sc.x + P.fsF, vlo = sc.y + (-P.fsF), vhi = sc.y + P.fsF;
@@ -596,21 +608,15 @@ __global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blocker
     }
 }
 
-// PCF visibility of every pixel of the band (shadow.cpp:47-63, 120-124): one warp per pixel
-__global__ void __launch_bounds__(256) k_pcf_visibility(ChainPass P, int row0, int row1, const float2* disk, float filterSize, float* vis)
+// PCF visibility (shadow.cpp:47-63, 120-124): site i consumes accepted disk samples 64 i .. 64 i + 63; one warp per site
+__global__ void __launch_bounds__(256) k_pcf_visibility(ShadowMapD sm, size_t first, size_t last, const float4* sc4, const float2* disk, float filterSize,
+                                                       float* vis)
 {
-    size_t n = (size_t)P.W * P.H;
     int    lane = threadIdx.x & 31;
-    size_t idx = (size_t)row0 * P.W + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (idx >= (size_t)row1 * P.W) return;
-    V3     pos = v3(P.worldpos[idx], P.worldpos[n + idx], P.worldpos[2 * n + idx]);
-    V3     nrm = v3(P.normal[idx], P.normal[n + idx], P.normal[2 * n + idx]);
-    V3     ln = v3(P.lndc[idx], P.lndc[n + idx], P.lndc[2 * n + idx]);
-    V3     lightDir = vnormalize(vsub(v3(P.lightPos[0], P.lightPos[1], P.lightPos[2]), pos));
-    V3     sc = vadd(vscale(ln, 0.5f), v3(0.5f, 0.5f, 0.5f));
-    float  bias = fmaxf(P.biasSlope * (1.f - vdot(nrm, lightDir)), P.biasMin);
+    size_t idx = first + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (idx >= last) return;
     float2 d1 = __ldg(disk + idx * 64 + lane), d2 = __ldg(disk + idx * 64 + 32 + lane);
-    float  v = pcf_taps(P.sm, make_float4(sc.x, sc.y, sc.z, bias), filterSize, d1, d2);
+    float  v = pcf_taps(sm, sc4[idx], filterSize, d1, d2);
     if (lane == 0) vis[idx] = v;
 }
 }  // namespace
@@ -765,10 +771,11 @@ static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
     return FGL_OK;
 }
 
-int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
+// Visibility of n stream consumers ("sites") in consumption order, given their shadow coordinate + bias.
+// [siteLo, siteHi) = the sites whose visibility is needed (PCF); PCSS resolves the whole chain.
+int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4In, size_t siteLo, size_t siteHi)
 {
     SampleStream*      s = S_of(c);
-    size_t             n = (size_t)L.W * L.H;
     cudaStream_t       st = c->stream;
     unsigned long long rawBegin = s->ssaoThisFrame ? s->ballRawEnd : 0ull;
     // PCF: 64 samples per pixel; PCSS: chunk index <= 3 n, plus the 96 samples of the last pixel
@@ -794,16 +801,13 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     L.vis = (const float*)s->vis.p;
 
     ChainPass P;
-    P.W = L.W, P.H = L.H;
-    P.worldpos = L.planes.p[FGL_PLANE_WORLDPOS], P.normal = L.planes.p[FGL_PLANE_NORMAL], P.lndc = L.planes.p[FGL_PLANE_LIGHTNDC];
-    memcpy(P.lightPos, L.lightPos, 12);
-    P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
-    P.smMin = P.smMax = nullptr, P.r = 0, P.fsF = 0.f;
+    memset(&P, 0, sizeof P);
+    P.sm = L.sm;
     if (!pcss)
     {
-        size_t      nPix = (size_t)L.W * (L.row1 - L.row0);
-        LaunchScope ls(c, "pcf_visibility", nPix * (36 + 512 + 4));
-        k_pcf_visibility<<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, st>>>(P, L.row0, L.row1, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
+        size_t      nSites = siteHi - siteLo;
+        LaunchScope ls(c, "pcf_visibility", nSites * (16 + 512 + 4));
+        if (nSites) k_pcf_visibility<<<(unsigned)((nSites * 32 + 255) / 256), 256, 0, st>>>(L.sm, siteLo, siteHi, sc4In, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
         return FGL_OK;
     }
 
@@ -812,7 +816,6 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     DevBuf* f4[] = { &s->smTmpMin, &s->smTmpMax, &s->smMin, &s->smMax, &s->boxMin, &s->boxMax };
     for (DevBuf* b : f4)
         if (int rc = fgl_reserve(c, *b, smN * 4)) return rc;
-    if (int rc = fgl_reserve(c, s->sc4, n * 16)) return rc;
     DevBuf* i4[] = { &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->hasB, &s->kpre, &s->blockerList };
     for (DevBuf* b : i4)
         if (int rc = fgl_reserve(c, *b, (n + 1) * 4)) return rc;
@@ -835,8 +838,8 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     P.smMin = (const float*)s->smMin.p, P.smMax = (const float*)s->smMax.p, P.r = r, P.fsF = fsF;
     unsigned nb = (unsigned)((n + 255) / 256);
     {
-        LaunchScope ls(c, "pcss_classify", n * (36 + 16 + 8));
-        k_classify<<<nb, 256, 0, st>>>(P, (float4*)s->sc4.p, (int*)s->isU.p, (int*)s->isC1.p);
+        LaunchScope ls(c, "pcss_classify", n * (16 + 8));
+        k_classify<<<nb, 256, 0, st>>>(P, n, sc4In, (int*)s->isU.p, (int*)s->isC1.p);
     }
     FGL_CUDA(c, cudaMemsetAsync((int*)s->isU.p + n, 0, 4, st));
     if (int rc = scan_ints(c, (const int*)s->isU.p, (int*)s->posU.p, n + 1)) return rc;
@@ -855,7 +858,7 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     {
         {
             LaunchScope ls(c, "pcss_gather", n * 12);
-            k_gather_uncertain<<<nb, 256, 0, st>>>(n, (const int*)s->isU.p, (const int*)s->posU.p, (const int*)s->c1pre.p, (const float4*)s->sc4.p,
+            k_gather_uncertain<<<nb, 256, 0, st>>>(n, (const int*)s->isU.p, (const int*)s->posU.p, (const int*)s->c1pre.p, sc4In,
                                                    (unsigned*)s->Upix.p, (unsigned*)s->Uc1.p, (float4*)s->Usc.p);
         }
         {
@@ -917,11 +920,32 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     }
     {
         LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
-        k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, (const float4*)s->sc4.p,
+        k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
                                                    (const unsigned*)s->chunkOf.p, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, (float*)s->vis.p);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("pcss chain: ") + cudaGetErrorString(e));
     return FGL_OK;
+}
+
+// Deferred lighting: the sites are the pixels in scan order (forkergl.cpp:336-378 visits every pixel, background included).
+int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
+{
+    SampleStream* s = S_of(c);
+    size_t        n = (size_t)L.W * L.H;
+    if (int rc = fgl_reserve(c, s->sc4, n * 16)) return rc;
+    ChainPass P;
+    memset(&P, 0, sizeof P);
+    P.W = L.W, P.H = L.H;
+    P.worldpos = L.planes.p[FGL_PLANE_WORLDPOS], P.normal = L.planes.p[FGL_PLANE_NORMAL], P.lndc = L.planes.p[FGL_PLANE_LIGHTNDC];
+    memcpy(P.lightPos, L.lightPos, 12);
+    P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
+    bool   pcss = L.shadowMode == FGL_SHADOW_PCSS;
+    size_t lo = pcss ? 0 : (size_t)L.row0 * L.W, hi = pcss ? n : (size_t)L.row1 * L.W;  // the PCSS chain needs every earlier pixel
+    {
+        LaunchScope ls(c, "shadow_coords", (hi - lo) * (36 + 16));
+        k_shadow_coords<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(P, lo, hi, (float4*)s->sc4.p);
+    }
+    return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, (size_t)L.row0 * L.W, (size_t)L.row1 * L.W);
 }

@@ -11,3 +11,5 @@ int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S);
 // 64 more iff the pixel's blocker search found a blocker (shadow.cpp:92-106) — a frame-long dependency chain that
 // is resolved here into a per-pixel chunk index.
 int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L);
+// Generic form: n consumers in consumption order with their shadow coordinate + bias (device array); leaves L.vis set.
+int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4, size_t siteLo, size_t siteHi);

@@ -9,7 +9,7 @@ from conftest import COLOUR_MAX_LSB, COLOUR_MIN_FRACTION_WITHIN_1LSB, EXACT_PLAN
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c4_hard", "c4_catbox_linear", "pbr_hard", "c3_pcss_ssao"]
+CONFIGS = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c2_pcf", "c4_hard", "c4_catbox_linear", "pbr_hard", "c3_pcss_ssao"]
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)

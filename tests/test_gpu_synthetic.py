@@ -24,6 +24,9 @@ CASES = {
     "ssaa3_odd": dict(shadow_mode=B.SHADOW_HARD, ssaa=3, size=(101, 67)),
     "no_shadow": dict(shadow_mode=B.SHADOW_HARD, shadow=False),
     "forward_hard": dict(shadow_mode=B.SHADOW_HARD, forward=True),
+    "forward_pcf": dict(shadow_mode=B.SHADOW_PCF, forward=True),
+    "forward_pcss": dict(shadow_mode=B.SHADOW_PCSS, forward=True, size=(300, 180)),
+    "forward_pcf_dense": dict(shadow_mode=B.SHADOW_PCF, forward=True, quads=96, size=(200, 120)),
     "odd_size_pcss": dict(shadow_mode=B.SHADOW_PCSS, ssao=True, size=(333, 211)),
     "dense_mesh": dict(shadow_mode=B.SHADOW_PCSS, quads=160, size=(256, 160)),
 }
