@@ -37,6 +37,7 @@ WORKLOADS = {
     "c1_ssao": ("scenes/c1_ssao.scene", "pcss", 0, 0, "scenes/c1_ssao.scene: Mary + plane, 1280x800 deferred, PCSS + SSAO"),
     "c3": ("scenes/c3.scene", "pcss", 0, 0, "scenes/c3.scene: plane + Mary + diablo_pose + great_sword, 3840x2160 deferred, PCSS + SSAO (two-pass Gaussian)"),
     "c3_pbr": ("scenes/c3_pbr.scene", "pcss", 0, 0, "scenes/c3_pbr.scene: C3 + chalkboard (Cook-Torrance), 3840x2160 deferred, PCSS + SSAO"),
+    "c2": ("scenes/c2.scene", "pcf", 0, 0, "scenes/c2.scene: plane + african_head, 1920x1080 forward Blinn-Phong + normal/specular maps, PCF"),
     "c4": ("scenes/c4_catbox.scene", "hard", 1, 1, "scenes/c4_catbox.scene: SSAA 2x (2560x1600 raster), Repeat + Linear textures"),
 }
 ASSETS = os.path.join(REPO, "oracle", "_ref", "assets")
@@ -118,51 +119,109 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    factor = cpu_factor(args.workload)
-    times, w, h = time_reference(args.workload, args.warmup + args.steps, factor)
-    t = times[args.warmup:]
-    ms = 1e3 * sum(t) / len(t)
-    mpx = w * h / 1e6 / (ms / 1e3)
-    sample = "%s at %dx%d (1/%d linear resolution), %d frames, single thread" % (WORKLOADS[args.workload][0], w, h, factor, len(t))
+    if args.workload in SYNTH:
+        ts = [time_oracle_port(args.workload) for _ in range(args.steps)]
+        w, h = ts[0][1], ts[0][2]
+        ms = 1e3 * sum(t[0] for t in ts) / len(ts)
+        mpx = w * h / 1e6 / (ms / 1e3)
+        sample = "oracle port on the synthetic scene reduced to %d triangles at %dx%d, %d frames, single thread" % (ts[0][3], w, h, len(ts))
+        kind, desc = "port", SYNTH[args.workload][4]
+    else:
+        factor = cpu_factor(args.workload)
+        times, w, h = time_reference(args.workload, args.warmup + args.steps, factor)
+        t = times[args.warmup:]
+        ms = 1e3 * sum(t) / len(t)
+        mpx = w * h / 1e6 / (ms / 1e3)
+        sample = "%s at %dx%d (1/%d linear resolution), %d frames, single thread" % (WORKLOADS[args.workload][0], w, h, factor, len(t))
+        kind, desc = "reference", WORKLOADS[args.workload][4]
     line = {"impl": "reference", "metric": "mpixels_per_s", "value": mpx, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "reference assets (obj/*), synthetic camera/light of the scene file",
-            "config": {"workload": WORKLOADS[args.workload][4], "sample": sample},
+            "config": {"workload": desc, "sample": sample},
             "frames_per_s": 1e3 / ms,
-            "cpu_baseline": {"value": mpx, "unit": "Mpixels/s", "cores": 1, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": mpx, "unit": "Mpixels/s", "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": mpx, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+SYNTH = {
+    # name: (quads per side, width, height, render kwargs, description, cpu sample (quads, width, height))
+    "c5": (2237, 7680, 4320, dict(shadow_mode=2, ssao=True), "synthetic 10.0 M-triangle height field + plane, deferred PBR, PCSS + SSAO, 7680x4320",
+           (280, 960, 540)),
+    "c5_small": (700, 1920, 1080, dict(shadow_mode=2, ssao=True), "synthetic 0.98 M-triangle height field + plane, deferred PBR, PCSS + SSAO, 1920x1080",
+                 (175, 480, 270)),
+}
+
+
+def make_renderer(args, local):
+    from forkerrenderer_b200 import binding as B
+    from forkerrenderer_b200 import multigpu as M
+    if args.workload in SYNTH:
+        from forkerrenderer_b200.synthetic import SyntheticScene
+        quads, W, H, kw, desc, _ = SYNTH[args.workload]
+        fgl = B.product_fgl(local)
+        scene = SyntheticScene(fgl, quads=quads, pbr=True, tex_size=256)
+        r = M.SyntheticRenderer(scene, W, H, materialize_frame_f32=False, **kw)
+        info = dict(desc=desc, triangles=scene.triangles, out_w=W, out_h=H, ssaa=False, free=lambda: None)
+        return r, info
+    scene_file, shadow, wrap, filt, desc = WORKLOADS[args.workload]
+    host = B.product_host()
+    sc = host.load_scene(os.path.join(REPO, scene_file), ASSETS, wrap, filt)
+    r = M.FacadeRenderer(host, sc, shadow, materialize=False)
+    info = dict(desc=desc, triangles=sc.triangles, out_w=sc.width, out_h=sc.height, ssaa=bool(sc.ssaa), free=sc.free)
+    return r, info
+
+
+def time_oracle_port(workload):
+    """C5 has no .scene file the reference could load: its CPU baseline is the oracle port on a reduced sample."""
+    from forkerrenderer_b200 import binding as B
+    from forkerrenderer_b200.synthetic import SyntheticScene
+    quads, W, H = SYNTH[workload][5]
+    orc = B.Fgl(os.path.join(REPO, "oracle", "liboracle.so"))
+    scene = SyntheticScene(orc, quads=quads, pbr=True, tex_size=256)
+    t0 = time.perf_counter()
+    scene.render(W, H, **SYNTH[workload][3])
+    orc.read_plane("frame_u8")
+    dt = time.perf_counter() - t0
+    orc.close()
+    return dt, W, H, scene.triangles
 
 
 def run_ours(args):
     import numpy as np
     import torch
     from forkerrenderer_b200 import binding as B
+    from forkerrenderer_b200 import multigpu as M
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     os.environ["FGL_DEVICE"] = str(local)
 
-    scene_file, shadow, wrap, filt, desc = WORKLOADS[args.workload]
-    host = B.product_host()
-    fgl = host.fgl
-    sc = host.load_scene(os.path.join(REPO, scene_file), ASSETS, wrap, filt)
-    W, H = sc.width, sc.height
-    out_px = W * H
+    r, info = make_renderer(args, local)
+    fgl = r.fgl
+    W, H = r.width, r.height            # raster size (output size x SSAA factor)
+    out_px = info["out_w"] * info["out_h"]
+    stream = torch.cuda.Stream()
+    fgl.set_stream(stream.cuda_stream)
+    comm = M.TorchComm(dist, torch.device("cuda", local)) if world > 1 else None
+    r0, r1, per = M.band_rows(H, world, rank)
+    band = torch.empty((per, W, 3), dtype=torch.uint8, device="cuda") if world > 1 else None
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         fgl.sync()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
     # L2 flush between timed iterations for workloads whose planes could sit in the 126 MB L2
-    plane_bytes = sc.buffer_width * sc.buffer_height * 100
+    plane_bytes = W * H * 100 // world
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if plane_bytes < (512 << 20) else None
 
     def flush_l2():
@@ -170,28 +229,28 @@ def run_ours(args):
             flush_buf.fill_(1)
             torch.cuda.synchronize()
 
-    def frame(materialize=False):
-        host.render(sc, shadow, materialize)
+    def frame(gather=True):
+        """One frame; with several GPUs: this rank's band, the chain hand-off, and the NCCL gather of the 8-bit bands."""
+        with torch.cuda.stream(stream):
+            M.render_frame(r, rank, world, comm, band_out=(band.data_ptr(), band.numel()) if world > 1 else None)
+            if world > 1 and gather:
+                return M.gather_bands(dist, torch, band, H, W, world)
+        return None
 
-    launches0 = fgl.launch_count()
     for _ in range(args.warmup):
         frame()
     barrier()
 
-    # ---- device-timed region: K frames, each bracketed by CUDA events on the library's stream -----------------
-    stream = torch.cuda.Stream()
-    fgl.set_stream(stream.cuda_stream)
-    for _ in range(2):
-        frame()
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
     l0 = fgl.launch_count()
     ev = []
-    barrier()
     for _ in range(args.steps):
         flush_l2()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         frame()
@@ -199,32 +258,40 @@ def run_ours(args):
         ev.append((e0, e1))
     barrier()
     launches = fgl.launch_count() - l0
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    ms = sum(ms_steps) / len(ms_steps)
+    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
 
-    # ---- end to end: facade call + read of the 8-bit frame into host memory, wall clock ------------------------
-    h2d = 0
+    # ---- end to end: facade call(s) + the finished 8-bit frame in host memory, wall clock --------------------------
     e2e_t = []
+    d2h = 0
     for i in range(args.steps + 1):
         flush_l2()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        frame()
-        img = fgl.read_plane("ssaa_u8" if sc.ssaa else "frame_u8")
+        full = frame()
+        if world > 1:
+            stream.synchronize()
+            if rank == 0:
+                img = full.cpu()
+                d2h = img.numel()
+        else:
+            img = fgl.read_plane("ssaa_u8" if info["ssaa"] else "frame_u8")
+            d2h = int(img.nbytes)
         t1 = time.perf_counter()
         if i:
             e2e_t.append(t1 - t0)
     e2e_ms = 1e3 * sum(e2e_t) / len(e2e_t)
-    d2h = int(img.nbytes)
-    n_draws = 0
     clocks = sampler.finish()
 
     # ---- per-kernel breakdown (library instrumentation, separate frames) -----------------------------------------
+    barrier()
     fgl.enable_timing(True)
     fgl.reset_timings()
     nprof = 3
     for _ in range(nprof):
         flush_l2()
-        frame()
+        frame(gather=False)
     fgl.sync()
     kern = fgl.timings()
     fgl.enable_timing(False)
@@ -233,13 +300,16 @@ def run_ours(args):
         k["ms_per_frame"] = k["ms_total"] / nprof
     kern.sort(key=lambda k: -k["ms_total"])
     peak, peak_src = measured_peaks()
-    top = next((k for k in kern if k["algorithmic_bytes"] > 0), kern[0])
+    byte_kernels = [k for k in kern if k["algorithmic_bytes"] > 0]
+    top = byte_kernels[0] if byte_kernels else kern[0]
     t_launch = top["ms_total"] / top["launches"] / 1e3
     bytes_launch = top["algorithmic_bytes"] / top["launches"]
     achieved = bytes_launch / t_launch / 1e9
+    total_kernel_ms = max(1e-9, sum(k["ms_per_frame"] for k in kern))
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
-                "avg_launch_ms": t_launch * 1e3, "share_of_frame": top["ms_per_frame"] / max(1e-9, sum(k["ms_per_frame"] for k in kern))}
+                "avg_launch_ms": t_launch * 1e3, "share_of_frame": top["ms_per_frame"] / total_kernel_ms,
+                "note": "largest bandwidth-bound kernel; the per-kernel table is in `kernels` (kernels without a byte figure are latency/ALU bound)"}
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device="cuda")
@@ -249,25 +319,31 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            factor = cpu_factor(args.workload)
-            times, cw, ch = time_reference(args.workload, 1, factor)
-            cpu = {"value": cw * ch / 1e6 / times[0], "unit": "Mpixels/s", "cores": 1, "kind": "reference",
-                   "sample": "%s at %dx%d (1/%d linear resolution), 1 frame of oracle/_ref/ref_driver, single thread (the reference has no threads)"
-                             % (scene_file, cw, ch, factor), "ms_per_frame": 1e3 * times[0]}
+            if args.workload in SYNTH:
+                dt, cw, ch, ctris = time_oracle_port(args.workload)
+                cpu = {"value": cw * ch / 1e6 / dt, "unit": "Mpixels/s", "cores": 1, "kind": "port", "ms_per_frame": 1e3 * dt,
+                       "sample": "oracle port (oracle/liboracle.so) on the same synthetic scene reduced to %d triangles at %dx%d, 1 frame, single thread" % (ctris, cw, ch)}
+            else:
+                factor = cpu_factor(args.workload)
+                times, cw, ch = time_reference(args.workload, 1, factor)
+                cpu = {"value": cw * ch / 1e6 / times[0], "unit": "Mpixels/s", "cores": 1, "kind": "reference", "ms_per_frame": 1e3 * times[0],
+                       "sample": "%s at %dx%d (1/%d linear resolution), 1 frame of oracle/_ref/ref_driver, single thread (the reference has no threads)"
+                                 % (WORKLOADS[args.workload][0], cw, ch, factor)}
         line = {"metric": "mpixels_per_s", "value": out_px / 1e6 / (ms / 1e3), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "reference assets (obj/*), camera/light of the scene file",
-                "config": {"workload": desc, "triangles": sc.triangles, "width": W, "height": H,
-                           "l2": "explicit 256 MiB flush between timed frames" if flush_buf is not None else "planes (%.0f MB) exceed the 126 MB L2" % (plane_bytes / 1e6)},
+                "vs_baseline": None, "dtype": "f32", "data": "reference assets (obj/*) / procedural mesh, camera and light of the scene",
+                "config": {"workload": info["desc"], "triangles": info["triangles"], "width": info["out_w"], "height": info["out_h"],
+                           "partition": "sort-first row bands, %d rows per GPU, geometry replicated, RGB8 bands all-gathered with NCCL" % per if world > 1 else "single GPU",
+                           "l2": "explicit 256 MiB flush between timed frames" if flush_buf is not None else "planes (%.0f MB per GPU) exceed the 126 MB L2" % (plane_bytes / 1e6)},
                 "frames_per_s": 1e3 / ms,
                 "e2e": {"value": out_px / 1e6 / (e2e_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(h2d_bytes(sc)), "d2h_bytes_per_step": d2h},
+                        "h2d_bytes_per_step": 2 * 512 * 8, "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "kernels": [{"name": k["name"], "ms_per_frame": round(k["ms_per_frame"], 4), "launches_per_frame": k["launches"] / nprof,
                              "gbps": (k["algorithmic_bytes"] / max(1e-12, k["ms_total"] / 1e3) / 1e9) if k["algorithmic_bytes"] else None}
                             for k in kern]}
         print(json.dumps(line))
-    sc.free()
+    info["free"]()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -283,7 +359,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(SYNTH))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -193,6 +193,13 @@ class Fgl:
     def set_shadow_status(self, on): self.call("fgl_set_shadow_status", int(bool(on)))
     def begin_frame(self): self.call("fgl_begin_frame")
     def set_row_band(self, y0, y1): self.call("fgl_set_row_band", int(y0), int(y1))
+    def set_chain_blockers_before(self, k): self.call("fgl_set_chain_blockers_before", C.c_uint64(int(k)))
+
+    def get_chain_blockers(self):
+        v = C.c_uint64(0)
+        self.call("fgl_get_chain_blockers", C.byref(v))
+        return v.value
+
     def draw_mesh(self, mesh_id, kind, uniforms): self.call("fgl_draw_mesh", int(mesh_id), int(kind), C.byref(uniforms))
     def ssao(self): self.call("fgl_ssao")
     def blur(self, plane, kind): self.call("fgl_blur", int(plane), int(kind))
@@ -277,6 +284,8 @@ class Host:
         self.lib.frh_scene_free.argtypes = [C.c_void_p]
         self.lib.frh_scene_free.restype = None
         self.lib.frh_render.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.lib.frh_render_begin.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.lib.frh_render_finish.argtypes = [C.c_void_p]
         self.lib.frh_scene_info.argtypes = [C.c_void_p, C.c_void_p]
         self.lib.frh_set_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         self._fgl = None
@@ -308,6 +317,14 @@ class Host:
         if isinstance(shadow_mode, str):
             shadow_mode = SHADOW_MODES[shadow_mode]
         self._ck(self.lib.frh_render(scene.handle, int(shadow_mode), int(bool(materialize_frame_f32))), "frh_render")
+
+    def render_begin(self, scene, shadow_mode=SHADOW_PCSS, materialize_frame_f32=True):
+        if isinstance(shadow_mode, str):
+            shadow_mode = SHADOW_MODES[shadow_mode]
+        self._ck(self.lib.frh_render_begin(scene.handle, int(shadow_mode), int(bool(materialize_frame_f32))), "frh_render_begin")
+
+    def render_finish(self, scene):
+        self._ck(self.lib.frh_render_finish(scene.handle), "frh_render_finish")
 
     def set_camera(self, scene, eye, look_at):
         self._ck(self.lib.frh_set_camera(scene.handle, (C.c_float * 3)(*eye), (C.c_float * 3)(*look_at)),

@@ -96,6 +96,14 @@ void band_of(fgl_ctx* c, int H, int& r0, int& r1)
     r0 = std::max(0, std::min(c->row0, H));
     r1 = c->row1 < 0 ? H : std::max(r0, std::min(c->row1, H));
 }
+// Rows whose G-buffer / AO a band needs beyond itself: the V blur is warmed up over kBlurWarm rows above the band and
+// looks 4 rows ahead; the H blur and SSAO must therefore cover [r0 - kBlurWarm, r1 + 4).
+constexpr int kBlurWarm = 64, kBlurAhead = 4;
+void halo_band_of(fgl_ctx* c, int H, int& r0, int& r1)
+{
+    band_of(c, H, r0, r1);
+    r0 = std::max(0, r0 - kBlurWarm), r1 = std::min(H, r1 + kBlurAhead);
+}
 
 PlanesD planes_dev(fgl_ctx* c)
 {
@@ -151,7 +159,11 @@ int flush(fgl_ctx* c)
     memset(&P, 0, sizeof P);
     P.W = target.w, P.H = target.h;
     P.row0 = 0, P.row1 = P.H;
-    if (!shadowPass) band_of(c, P.H, P.row0, P.row1);
+    if (!shadowPass)
+    {
+        if (c->pass == FGL_PASS_GEOMETRY) halo_band_of(c, P.H, P.row0, P.row1);
+        else band_of(c, P.H, P.row0, P.row1);
+    }
     P.passType = c->pass, P.shadowOn = c->shadowOn;
     memcpy(P.viewport, c->viewport, sizeof P.viewport);
     size_t  nPix = (size_t)P.W * P.H;
@@ -253,7 +265,7 @@ int flush(fgl_ctx* c)
     const float4* sc4 = nullptr;
     if ((rc = fgl_run_forward_sites(c, P, L, &nSites, &sc4))) return rc;
     if (nSites)
-        if ((rc = fgl_stream_site_visibility(c, L, nSites, sc4, 0, nSites))) return rc;
+        if ((rc = fgl_stream_site_visibility(c, L, nSites, sc4, 0, nSites, 0))) return rc;
     return fgl_run_resolve_forward(c, P, planes_dev(c), L);
 }
 
@@ -518,6 +530,21 @@ int fgl_begin_frame(fgl_ctx* c)
     fgl_stream_begin_frame(c);
     return FGL_OK;
 }
+int fgl_set_chain_blockers_before(fgl_ctx* c, uint64_t blockers)
+{
+    ENTER(c);
+    c->chainBlockersBefore = blockers;
+    return FGL_OK;
+}
+int fgl_get_chain_blockers(fgl_ctx* c, uint64_t* out)
+{
+    ENTER(c);
+    if (!out) return fgl_fail(c, FGL_ERR_INVALID, "out is NULL");
+    unsigned long long v = 0;
+    if (int rc = fgl_stream_chain_total(c, &v)) return rc;
+    *out = v;
+    return FGL_OK;
+}
 int fgl_set_row_band(fgl_ctx* c, int row0, int row1)
 {
     ENTER(c);
@@ -627,7 +654,7 @@ int fgl_ssao(fgl_ctx* c)
     SsaoPass S;
     memset(&S, 0, sizeof S);
     S.W = frame.w, S.H = frame.h;
-    band_of(c, S.H, S.row0, S.row1);
+    halo_band_of(c, S.H, S.row0, S.row1);
     S.worldpos = (const float*)c->planes[FGL_PLANE_WORLDPOS].buf.p, S.normal = (const float*)c->planes[FGL_PLANE_NORMAL].buf.p;
     S.depth = (const float*)dp.buf.p, S.ao = (float*)c->planes[FGL_PLANE_AO].buf.p;
     memcpy(S.viewProj, c->viewProj, 64), memcpy(S.viewport, c->viewport, 64);
@@ -646,7 +673,11 @@ int fgl_blur(fgl_ctx* c, int plane, int kind)
     if (!p.buf.p) return fgl_fail(c, FGL_ERR_STATE, "fgl_blur: plane not initialised");
     if (int rc = materialize(c, plane)) return rc;
     if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = false;
-    return fgl_run_blur(c, (float*)p.buf.p, p.w, p.h, p.ch, kind);
+    int h0, h1, v0, v1;
+    halo_band_of(c, p.h, h0, h1);
+    band_of(c, p.h, v0, v1);
+    v0 = std::max(0, v0 - kBlurWarm);
+    return fgl_run_blur(c, (float*)p.buf.p, p.w, p.h, p.ch, kind, h0, h1, v0, v1);
 }
 
 int fgl_ssaa_resolve(fgl_ctx* c, int k)

@@ -129,6 +129,7 @@ struct fgl_ctx
     float        viewport[16], viewProj[16], lightSpace[16];
     int          mode = FGL_MODE_FORWARD, pass = FGL_PASS_FORWARD, shadowOn = 1;
     int          row0 = 0, row1 = -1;  // band; row1 < 0 = whole buffer
+    unsigned long long chainBlockersBefore = 0;  // sort-first: blockers found by the bands above this one (PCSS chain input)
 
     PlaneH planes[FGL_PLANE_AO + 1];
     DevBuf frameRgb8, ssaaRgb8;
@@ -206,7 +207,7 @@ int fgl_run_fill_rgb(fgl_ctx* c, float* dst, size_t nPixels, const float rgb[3])
 int fgl_run_lighting(fgl_ctx* c, const LightPass& L);
 int fgl_run_quantize(fgl_ctx* c, const float* frame, size_t nPixels, uint8_t* rgb8);
 int fgl_run_ssaa(fgl_ctx* c, const uint8_t* rgb8, int W, int H, int k, uint8_t* out, int row0, int row1);
-int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind);
+int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind, int hRow0, int hRow1, int vRow0, int vRow1);
 int fgl_run_ids(fgl_ctx* c, const unsigned long long* vis, size_t n, int* out);
 int fgl_run_aos(fgl_ctx* c, const float* soa, float* aos, size_t nPixels, int channels, bool toAos);
 struct SsaoPass

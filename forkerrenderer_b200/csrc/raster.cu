@@ -136,11 +136,6 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
     if (!tc.valid) flags = TRI_SKIP;
     // a triangle whose own bounding box misses the buffer only scans pixels outside itself (all rejected)
     if (sane && (mxx < 0 || mnx > P.W - 1 || mxy < 0 || mny > P.H - 1)) flags = TRI_SKIP;
-    if (!shadowPass)
-    {   // sort-first row band of this GPU
-        ymin = max(ymin, P.row0), ymax = min(ymax, P.row1 - 1);
-        if (ymin > ymax) flags = TRI_SKIP, ymin = ymax = 0;
-    }
     int bw = xmax - xmin + 1, bh = ymax - ymin + 1, nb = 0;
     if (!(flags & TRI_SKIP))
     {
@@ -413,14 +408,20 @@ __device__ __forceinline__ void load_vary(const TriVary* vary, int prim, float* 
 // gshader.h:95-201 + the G-buffer writes of forkergl.cpp:211-223
 __global__ void __launch_bounds__(128) k_resolve_geometry(RasterPass P, PlanesD out)
 {
-    int px = blockIdx.x * blockDim.x + threadIdx.x, py = P.row0 + blockIdx.y;
-    if (px >= P.W || py >= P.row1) return;
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    if (px >= P.W) return;
     size_t n = (size_t)P.W * P.H, idx = (size_t)px + (size_t)py * P.W;
     int    prim;
     V3     bary;
     float  depth;
     V3     z3 = v3(0.f, 0.f, 0.f);
-    if (!decode_winner(P, idx, px, py, prim, bary, depth))
+    bool   covered = decode_winner(P, idx, px, py, prim, bary, depth);
+    if (py < P.row0 || py >= P.row1)
+    {   // outside this GPU's band (+ halo): only the depth plane, which SSAO gathers from anywhere
+        out.p[FGL_PLANE_DEPTH][idx] = covered ? depth : 3.402823466e+38f;
+        return;
+    }
+    if (!covered)
     {
         out.p[FGL_PLANE_DEPTH][idx] = 3.402823466e+38f;
         st3(out.p[FGL_PLANE_NORMAL], n, idx, z3);
@@ -754,8 +755,8 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
         dim3 grid((P.W + 127) / 128, P.row1 - P.row0);
         if (P.passType == FGL_PASS_GEOMETRY)
         {
-            LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88);
-            k_resolve_geometry<<<grid, 128, 0, st>>>(P, planes);
+            LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88 + (uint64_t)P.W * (P.H - (P.row1 - P.row0)) * 12);
+            k_resolve_geometry<<<dim3((P.W + 127) / 128, P.H), 128, 0, st>>>(P, planes);
         }
         else if (P.passType == FGL_PASS_FORWARD && forwardLight)
         {

@@ -224,10 +224,10 @@ __device__ __forceinline__ float blur_step(BlurState& s, float x0, float x1, flo
 constexpr int kBlurTile = 128;
 // H pass: a CTA owns 32 rows; tiles of 128 columns (+4 look-ahead) are staged in shared memory with coalesced loads,
 // one warp (a lane per row) walks the recurrence, the tile is written back coalesced.
-__global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H)
+__global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H, int rowBegin)
 {
     __shared__ float tile[32][kBlurTile + 4 + 1];
-    const int row0 = blockIdx.x * 32;
+    const int row0 = rowBegin + blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     BlurState st;
     st.h1 = st.h2 = st.h3 = st.h4 = 0.f;
@@ -262,19 +262,23 @@ __global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H)
 }
 
 // V pass: one thread per column, rows walked in order; loads and stores are coalesced across the warp.
-__global__ void __launch_bounds__(64) k_blur_v(float* a, int W, int H)
+// rowBegin > 0 (sort-first band): the recurrence is warmed up from a row >= 64 above the band; its memory of the
+// start decays as 0.61^n, far below fp32 resolution after 64 rows.
+__global__ void __launch_bounds__(64) k_blur_v(float* a, int W, int H, int rowBegin, int rowEnd)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
-    float     x0 = a[x], x1 = a[(size_t)min(1, H - 1) * W + x], x2 = a[(size_t)min(2, H - 1) * W + x], x3 = a[(size_t)min(3, H - 1) * W + x];
+    const int b = rowBegin;
+    float     x0 = a[(size_t)b * W + x], x1 = a[(size_t)min(b + 1, H - 1) * W + x], x2 = a[(size_t)min(b + 2, H - 1) * W + x],
+          x3 = a[(size_t)min(b + 3, H - 1) * W + x];
     BlurState st;
     st.h1 = st.h2 = st.h3 = st.h4 = x0;
-    for (int h = 0; h < H; ++h)
+    for (int h = b; h < rowEnd; ++h)
     {
         // a[min(h+4, H-1)] is still original: rows below h have not been written yet (at the bottom edge the
         // clamped taps re-read the not yet overwritten last row, exactly as the in-place loop does)
         float x4 = (h + 4 <= H - 1) ? a[(size_t)(h + 4) * W + x] : x3;  // x3 already holds the last row when clamping
-        float r = blur_step(st, x0, x1, x2, x3, x4, h == 0);
+        float r = blur_step(st, x0, x1, x2, x3, x4, h == b);
         a[(size_t)h * W + x] = r;
         x0 = x1, x1 = x2, x2 = x3, x3 = x4;
     }
@@ -395,7 +399,7 @@ int fgl_run_ssaa(fgl_ctx* c, const uint8_t* rgb8, int W, int H, int k, uint8_t* 
     return check_launch(c, "ssaa");
 }
 
-int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind)
+int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind, int hRow0, int hRow1, int vRow0, int vRow1)
 {
     if (kind != FGL_BLUR_TWO_PASS_GAUSSIAN)
         return fgl_fail(c, FGL_ERR_UNSUPPORTED, "fgl_blur: the in-place 3x3 box (buffer.cpp:35-57) is not on the frame path and has no device kernel yet");
@@ -404,11 +408,11 @@ int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind)
     {
         {
             LaunchScope ls(c, "blur_h", n * 8);
-            k_blur_h<<<(H + 31) / 32, 256, 0, c->stream>>>(plane + ch * n, W, H);
+            k_blur_h<<<(hRow1 - hRow0 + 31) / 32, 256, 0, c->stream>>>(plane + ch * n, W, hRow1, hRow0);
         }
         {
             LaunchScope ls(c, "blur_v", n * 8);
-            k_blur_v<<<(W + 63) / 64, 64, 0, c->stream>>>(plane + ch * n, W, H);
+            k_blur_v<<<(W + 63) / 64, 64, 0, c->stream>>>(plane + ch * n, W, H, vRow0, vRow1);
         }
     }
     return check_launch(c, "blur");

@@ -337,6 +337,7 @@ struct ChainRows
     ShadowMapD                sm;
     const float2*             disk;
     double                    fs;
+    unsigned long long        base;  // chunk of site i with k earlier blockers = base + i + 2 k
 };
 
 // flags of up to 32 (row, chunk) pairs, one per lane: signature tests first, then the warp evaluates the ambiguous
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot)
     int  lane = threadIdx.x & 31;
     int  j = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = j < R.nU;
-    size_t chunk = valid ? (size_t)R.Upix[j] + 2 * ((size_t)R.Uc1[j] + (size_t)(j >> 1)) : 0;
+    size_t chunk = valid ? (size_t)R.base + R.Upix[j] + 2 * ((size_t)R.Uc1[j] + (size_t)(j >> 1)) : 0;
     uint32_t w = eval_pairs(R, valid, j, chunk, lane);
     if (valid) pilot[j] = (w >> lane) & 1u;
 }
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(256) k_chain_eval(ChainRows R, const unsigned*
     int      lo = max(0, dhat - kWin / 2);
     int      d = lo + 32 * half + lane;
     bool     valid = d <= t;
-    size_t   chunk = (size_t)R.Upix[j] + 2 * ((size_t)R.Uc1[j] + m0 + (size_t)d);
+    size_t   chunk = (size_t)R.base + R.Upix[j] + 2 * ((size_t)R.Uc1[j] + m0 + (size_t)d);
     uint32_t w = eval_pairs(R, valid, j, chunk, lane);
     if (lane == 0)
     {
@@ -556,12 +557,12 @@ __global__ void __launch_bounds__(256) k_pixel_flags(size_t n, const int* isU, c
     hasBlocker[idx] = isU[idx] ? (int)flagU[posU[idx]] : isC1[idx];
 }
 // chunk index of every pixel, visibility 1 for the pixels without a blocker (shadow.cpp:96-99), list of the others
-__global__ void __launch_bounds__(256) k_chunk_index(size_t n, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis, unsigned* blockerList,
-                                                     unsigned* nBlockers)
+__global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long long base, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis,
+                                                     unsigned* blockerList, unsigned* nBlockers)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    chunkOf[idx] = (unsigned)idx + 2u * (unsigned)kpre[idx];
+    chunkOf[idx] = (unsigned)(base + idx + 2ull * (unsigned)kpre[idx]);
     vis[idx] = 1.f;
     if (hasB[idx]) blockerList[kpre[idx]] = (unsigned)idx;
     if (idx == n - 1) *nBlockers = (unsigned)(kpre[idx] + hasB[idx]);
@@ -638,6 +639,8 @@ struct SampleStream
     DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
     DevBuf sig, vis, blockerList, pilot, Ppre, winLo;
     unsigned long long sigChunks = 0;
+    unsigned long long chainBlockersBefore = 0;
+    bool               chainCountValid = false;
 };
 
 static SampleStream* S_of(fgl_ctx* c)
@@ -773,8 +776,10 @@ static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
 
 // Visibility of n stream consumers ("sites") in consumption order, given their shadow coordinate + bias.
 // [siteLo, siteHi) = the sites whose visibility is needed (PCF); PCSS resolves the whole chain.
-int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4In, size_t siteLo, size_t siteHi)
+int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const float4* sc4All, size_t siteLo, size_t siteHi, unsigned long long blockersBefore)
 {
+    size_t n = nTotal;  // table sizes follow the whole site set; the kernels below work on [siteLo, siteHi)
+
     SampleStream*      s = S_of(c);
     cudaStream_t       st = c->stream;
     unsigned long long rawBegin = s->ssaoThisFrame ? s->ballRawEnd : 0ull;
@@ -807,9 +812,14 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4*
     {
         size_t      nSites = siteHi - siteLo;
         LaunchScope ls(c, "pcf_visibility", nSites * (16 + 512 + 4));
-        if (nSites) k_pcf_visibility<<<(unsigned)((nSites * 32 + 255) / 256), 256, 0, st>>>(L.sm, siteLo, siteHi, sc4In, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
+        if (nSites) k_pcf_visibility<<<(unsigned)((nSites * 32 + 255) / 256), 256, 0, st>>>(L.sm, siteLo, siteHi, sc4All, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
         return FGL_OK;
     }
+    // from here on: the sites of this context's band, locally indexed; site i is global site siteLo + i
+    n = siteHi - siteLo;
+    const float4*            sc4In = sc4All + siteLo;
+    float*                   visB = (float*)s->vis.p + siteLo;
+    const unsigned long long chunkBase = (unsigned long long)siteLo + 2ull * blockersBefore;
 
     // ---- PCSS chain --------------------------------------------------------------------------------------------
     size_t  smN = (size_t)L.sm.w * L.sm.h;
@@ -819,8 +829,9 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4*
     DevBuf* i4[] = { &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->hasB, &s->kpre, &s->blockerList };
     for (DevBuf* b : i4)
         if (int rc = fgl_reserve(c, *b, (n + 1) * 4)) return rc;
-    if (int rc = fgl_reserve(c, s->chunkOf, n * 4)) return rc;
+    if (int rc = fgl_reserve(c, s->chunkOf, nTotal * 4)) return rc;
     if (int rc = fgl_reserve(c, s->mState, 64)) return rc;
+    unsigned* chunkOfB = (unsigned*)s->chunkOf.p + siteLo;
 
     float fsF = (float)L.pcssFilter;
     if (!((double)fsF >= L.pcssFilter)) fsF = nextafterf(fsF, 1e30f);  // |(float)(d * fs)| <= fsF for |d| < 1
@@ -872,7 +883,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4*
         ChainRows R;
         R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
         R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p, R.sig = (const unsigned long long*)s->sig.p;
-        R.sm = L.sm, R.disk = L.disk, R.fs = L.pcssFilter;
+        R.sm = L.sm, R.disk = L.disk, R.fs = L.pcssFilter, R.base = chunkBase;
         if (int rc = fgl_reserve(c, s->pilot, (size_t)(nU + 1) * 4)) return rc;
         if (int rc = fgl_reserve(c, s->Ppre, (size_t)(nU + 1) * 4)) return rc;
         if (int rc = fgl_reserve(c, s->bits, (size_t)kT * 2 * 4)) return rc;
@@ -915,15 +926,16 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4*
     if (int rc = scan_ints(c, (const int*)s->hasB.p, (int*)s->kpre.p, n)) return rc;
     {
         LaunchScope ls(c, "pcss_chunk_index", n * 20);
-        k_chunk_index<<<nb, 256, 0, st>>>(n, (const int*)s->kpre.p, (const int*)s->hasB.p, (unsigned*)s->chunkOf.p, (float*)s->vis.p,
-                                          (unsigned*)s->blockerList.p, (unsigned*)s->mState.p + CH_NBLOCKERS);
+        k_chunk_index<<<nb, 256, 0, st>>>(n, chunkBase, (const int*)s->kpre.p, (const int*)s->hasB.p, chunkOfB, visB, (unsigned*)s->blockerList.p,
+                                          (unsigned*)s->mState.p + CH_NBLOCKERS);
     }
     {
         LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
         k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
-                                                   (const unsigned*)s->chunkOf.p, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, (float*)s->vis.p);
+                                                   chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, visB);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
+    s->chainBlockersBefore = blockersBefore, s->chainCountValid = true;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("pcss chain: ") + cudaGetErrorString(e));
     return FGL_OK;
@@ -942,10 +954,24 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     memcpy(P.lightPos, L.lightPos, 12);
     P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
     bool   pcss = L.shadowMode == FGL_SHADOW_PCSS;
-    size_t lo = pcss ? 0 : (size_t)L.row0 * L.W, hi = pcss ? n : (size_t)L.row1 * L.W;  // the PCSS chain needs every earlier pixel
+    size_t lo = (size_t)L.row0 * L.W, hi = (size_t)L.row1 * L.W;
+    (void)pcss;
     {
         LaunchScope ls(c, "shadow_coords", (hi - lo) * (36 + 16));
         k_shadow_coords<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(P, lo, hi, (float4*)s->sc4.p);
     }
-    return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, (size_t)L.row0 * L.W, (size_t)L.row1 * L.W);
+    // sort-first bands: the chain of this band starts from the number of blockers found in the bands before it
+    return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, lo, hi, c->chainBlockersBefore);
+}
+
+// Blockers found up to and including this context's band (= input of the next band's chain); blocks on the stream.
+int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out)
+{
+    SampleStream* s = S_of(c);
+    if (!s->chainCountValid || !s->mState.p) return fgl_fail(c, FGL_ERR_STATE, "no PCSS chain has run on this context");
+    unsigned nb = 0;
+    FGL_CUDA(c, cudaMemcpyAsync(&nb, (unsigned*)s->mState.p + CH_NBLOCKERS, 4, cudaMemcpyDeviceToHost, c->stream));
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = s->chainBlockersBefore + nb;
+    return FGL_OK;
 }

@@ -12,4 +12,5 @@ int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S);
 // is resolved here into a per-pixel chunk index.
 int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L);
 // Generic form: n consumers in consumption order with their shadow coordinate + bias (device array); leaves L.vis set.
-int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4, size_t siteLo, size_t siteHi);
+int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4, size_t siteLo, size_t siteHi, unsigned long long blockersBefore);
+int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out);

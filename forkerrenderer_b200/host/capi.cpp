@@ -114,6 +114,22 @@ int frh_render(void* scene, int shadow_mode, int materialize_frame_f32)
     });
 }
 
+// The same frame in two calls (sort-first multi-GPU: the PCSS chain state is exchanged between them).
+int frh_render_begin(void* scene, int shadow_mode, int materialize_frame_f32)
+{
+    return Guard([&] {
+        Scene* s = (Scene*)scene;
+        Shadow::SetShadowMode((Shadow::Mode)shadow_mode);
+        ForkerGL::Params().materialize_frame_f32 = materialize_frame_f32;
+        Render::Preconfigure(*s);
+        Render::RenderGeometryStage(*s);
+    });
+}
+int frh_render_finish(void* scene)
+{
+    return Guard([&] { Render::RenderLightingStage(*(Scene*)scene); });
+}
+
 // Output::* of the reference's main (main.cpp:43-52) into `dir`.
 int frh_output_tga(const char* dir)
 {

@@ -35,8 +35,9 @@ void Preconfigure(const Scene& scene)
     ForkerGL::TextureFilterMode(Texture::Nearest);
 }
 
-// reference render.cpp:40-58
-void Render(const Scene& scene)
+// reference render.cpp:40-58, split where a sort-first multi-GPU driver has to exchange the PCSS chain state
+// (fgl_set_chain_blockers_before) between the bands: everything up to the lighting loop, then the rest.
+void RenderGeometryStage(const Scene& scene)
 {
     fgl_ctx* ctx = ForkerGL::Context();
     FglParams params = ForkerGL::Params();
@@ -51,9 +52,24 @@ void Render(const Scene& scene)
     else
     {
         DoGeometryPass(scene);
-        DoLightingPass(scene);
+        // first half of DoLightingPass (reference render.cpp:195-209)
+        ForkerGL::InitFrameBuffer(BufferWidth(scene), BufferHeight(scene));
+        ForkerGL::SetPassType(ForkerGL::LightingPass);
+        ForkerGL::ClearColor(Color3(0.12f, 0.12f, 0.12f));  // overwritten by the lighting loop, as in the reference
+        if (scene.IsSSAOOn()) DoSSAO(scene);
     }
+}
+
+void RenderLightingStage(const Scene& scene)
+{
+    if (ForkerGL::GetRenderMode() != ForkerGL::Forward) ForkerGL::DrawScreenSpacePixels(scene);  // render.cpp:210
     DoSSAA(scene);
+}
+
+void Render(const Scene& scene)
+{
+    RenderGeometryStage(scene);
+    RenderLightingStage(scene);
 }
 
 // reference render.cpp:60-97

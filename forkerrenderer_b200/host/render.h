@@ -7,6 +7,8 @@ namespace Render
 {
 void Preconfigure(const Scene& scene);
 void Render(const Scene& scene);
+void RenderGeometryStage(const Scene& scene);  // shadow + raster (+ SSAO): everything before the lighting loop
+void RenderLightingStage(const Scene& scene);  // lighting loop + SSAA
 void DoShadowPass(const Scene& scene);
 void DoForwardPass(const Scene& scene);
 void DoGeometryPass(const Scene& scene);

@@ -129,10 +129,16 @@ class SyntheticScene:
     def meshes(self):
         return [(self.plane, self.plane_model), (self.field, self.field_model)]
 
-    def render(self, W, H, shadow_mode=B.SHADOW_HARD, ssao=False, ssaa=1, forward=False, shadow=True,
-               materialize_frame_f32=True, band=None):
+    def render(self, W, H, **kw):
         """The pass sequence of Render::Render (render.cpp:40-58) for a W x H output (raster size W*ssaa x H*ssaa)."""
+        self.render_begin(W, H, **kw)
+        self.render_finish()
+
+    def render_begin(self, W, H, shadow_mode=B.SHADOW_HARD, ssao=False, ssaa=1, forward=False, shadow=True,
+                     materialize_frame_f32=True, band=None):
+        """Everything before the lighting loop (a sort-first driver exchanges the PCSS chain state before render_finish)."""
         f = self.f
+        self._pending = (forward, ssaa)
         BW, BH = W * ssaa, H * ssaa
         p = f.default_params()
         p.shadow_mode = shadow_mode
@@ -177,6 +183,11 @@ class SyntheticScene:
             if ssao:
                 f.ssao()
                 f.blur(B.PLANE_AO, B.BLUR_TWO_PASS_GAUSSIAN)
+
+    def render_finish(self):
+        f = self.f
+        forward, ssaa = self._pending
+        if not forward:
             f.draw_screen_space_pixels(self.eye, self.light_pos, self.light_color)
         if ssaa > 1:
             f.ssaa_resolve(ssaa)

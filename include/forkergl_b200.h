@@ -173,9 +173,15 @@ int fgl_set_shadow_status(fgl_ctx* ctx, int on);                       /* Shadow
  * reference process renders exactly one frame, so every frame sees the stream from its seed. */
 int fgl_begin_frame(fgl_ctx* ctx);
 
-/* Sort-first multi-GPU: restrict every camera-space pass (raster resolve, SSAO, blur, lighting, SSAA) to
- * buffer rows [row_begin, row_end).  The shadow pass always covers the whole map.  (0, height) = everything. */
+/* Sort-first multi-GPU: restrict the camera-space shading passes (G-buffer resolve, SSAO, blur, lighting, SSAA) to
+ * buffer rows [row_begin, row_end) (plus the few halo rows SSAO and the blur recurrence need).  The shadow pass and
+ * the camera depth plane always cover the whole buffer (SSAO gathers depth anywhere).  (0, -1) = everything. */
 int fgl_set_row_band(fgl_ctx* ctx, int row_begin, int row_end);
+/* Sort-first PCSS: the sample-stream position of a band depends on how many pixels of the bands before it found a
+ * blocker (shadow.cpp:96-105).  Set that count before the lighting pass of a band; read the running total (count
+ * before + this band's) after it and hand it to the next band.  Both default to / start from 0 for a whole frame. */
+int fgl_set_chain_blockers_before(fgl_ctx* ctx, uint64_t blockers);
+int fgl_get_chain_blockers(fgl_ctx* ctx, uint64_t* out_blockers);
 
 /* ---- draw submission ------------------------------------------------------------------------------- */
 /* Mesh::Draw (src/mesh.cpp:10-25) for every face of the mesh: vertex program x3 + ForkerGL::DrawTriangle

@@ -872,6 +872,8 @@ int fgl_begin_frame(fgl_ctx* c)
     return FGL_OK;
 }
 int fgl_set_row_band(fgl_ctx*, int, int) { return FGL_OK; }  // the oracle always computes the whole frame
+int fgl_set_chain_blockers_before(fgl_ctx*, uint64_t) { return FGL_OK; }
+int fgl_get_chain_blockers(fgl_ctx* c, uint64_t*) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle renders whole frames"); }
 
 // ---- draws --------------------------------------------------------------------------------------------------
 int fgl_draw_mesh(fgl_ctx* c, int meshId, int kind, const FglUniforms* un)  // mesh.cpp:10-25

@@ -1,0 +1,42 @@
+"""Sort-first bands on ONE GPU: two contexts render the two halves of a frame one after the other, the second one
+starting its PCSS chain from the first one's blocker count — the result must equal the single-context frame bit for
+bit (this is the data path bench.py --gpus N runs with one process per GPU and NCCL in between)."""
+import numpy as np
+import pytest
+
+import parity as P
+from forkerrenderer_b200 import binding as B
+from forkerrenderer_b200 import multigpu as M
+from forkerrenderer_b200.synthetic import SyntheticScene
+
+pytestmark = pytest.mark.gpu
+
+
+class LocalComm:
+    def __init__(self):
+        self.box = {}
+
+    def send_int(self, v, dst):
+        self.box[dst] = v
+
+    def recv_int(self, src):
+        return self.box.pop(src + 1)
+
+
+@pytest.mark.parametrize("mode,ssao,world", [(B.SHADOW_PCSS, True, 2), (B.SHADOW_PCSS, False, 3), (B.SHADOW_PCF, True, 2), (B.SHADOW_HARD, True, 4)])
+def test_bands_equal_full_frame(mode, ssao, world, gpu_fgl):
+    W, H = 320, 240
+    full_scene = SyntheticScene(gpu_fgl, quads=40)
+    full_scene.render(W, H, shadow_mode=mode, ssao=ssao)
+    full = gpu_fgl.read_plane("frame_u8")
+    comm = LocalComm()
+    ctxs = [B.product_fgl(0) for _ in range(world)]
+    try:
+        for rank, f in enumerate(ctxs):
+            r = M.SyntheticRenderer(SyntheticScene(f, quads=40), W, H, shadow_mode=mode, ssao=ssao)
+            r0, r1 = M.render_frame(r, rank, world, comm)
+            got = f.read_plane("frame_u8")
+            assert np.array_equal(got[r0:r1], full[r0:r1]), "band %d of %d differs from the full frame" % (rank, world)
+    finally:
+        for f in ctxs:
+            f.close()

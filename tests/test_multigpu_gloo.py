@@ -1,0 +1,109 @@
+"""The N > 1 orchestration (band split, PCSS chain hand-off order, band gather) on CPU with the gloo backend,
+world_size 2 and 3.  The per-band renderer is a stand-in built from one whole-frame oracle render: what is tested here
+is the host-side logic of forkerrenderer_b200/multigpu.py, not the kernels (tests/test_gpu_synthetic.py checks that a
+band render equals the corresponding rows of the full frame on the GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import parity as P
+from forkerrenderer_b200 import binding as B
+from forkerrenderer_b200 import multigpu as M
+from forkerrenderer_b200.synthetic import SyntheticScene
+
+
+class FakeFgl:
+    """Band-restricted view of a finished whole frame: rows of the RGB8 image + a per-row 'blocker' count."""
+
+    def __init__(self, image, blockers_per_row):
+        self.image, self.per_row = image, blockers_per_row
+        self.before, self.band, self.log = None, None, []
+
+    def set_row_band(self, r0, r1):
+        self.band = (r0, r1)
+
+    def set_chain_blockers_before(self, k):
+        self.before = k
+        self.log.append(("before", k))
+
+    def get_chain_blockers(self):
+        return self.before + int(self.per_row[self.band[0]:self.band[1]].sum())
+
+    def copy_plane_rows_to_device(self, plane, r0, r1, ptr, nbytes):
+        assert plane == B.PLANE_FRAME_RGB8 and nbytes == (r1 - r0) * self.image.shape[1] * 3
+        ptr[: r1 - r0] = torch.from_numpy(self.image[r0:r1].copy())
+
+
+class FakeRenderer:
+    def __init__(self, fgl, pcss=True):
+        self.fgl, self.pcss = fgl, pcss
+        self.height, self.width = fgl.image.shape[:2]
+
+    def begin(self, band):
+        self.fgl.set_row_band(*band)
+
+    def finish(self):
+        assert not self.pcss or self.fgl.before is not None, "lighting started before the chain state arrived"
+
+
+class PtrFgl(FakeFgl):
+    pass
+
+
+def worker(rank, world, port, image, per_row, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fgl = FakeFgl(image, per_row)
+    r = FakeRenderer(fgl)
+    H, W = image.shape[:2]
+    r0, r1, per = M.band_rows(H, world, rank)
+    band = torch.zeros((per, W, 3), dtype=torch.uint8)
+    comm = M.TorchComm(dist, "cpu")
+    M.render_frame(r, rank, world, comm, band_out=(band, band.numel()))
+    full = M.gather_bands(dist, torch, band, H, W, world)
+    expected_before = int(per_row[:r0].sum())
+    ok = fgl.before == expected_before and np.array_equal(full.numpy(), image)
+    out.put((rank, ok, fgl.before, expected_before))
+    dist.destroy_process_group()
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_split_handoff_and_gather(world, oracle_fgl):
+    s = SyntheticScene(oracle_fgl)
+    s.render(64, 50, shadow_mode=B.SHADOW_PCSS)
+    image = oracle_fgl.read_plane("frame_u8")
+    rng = np.random.RandomState(1)
+    per_row = rng.randint(0, 40, size=image.shape[0])
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, image, per_row, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, before, expected in res:
+        assert ok, (rank, before, expected)
+
+
+def test_band_rows_cover_the_frame():
+    for H in (1, 7, 800, 2160, 4320):
+        for world in (1, 2, 3, 4, 8):
+            rows = [M.band_rows(H, world, r) for r in range(world)]
+            assert rows[0][0] == 0 and max(r[1] for r in rows) == H
+            assert all(rows[i][1] == rows[i + 1][0] or rows[i + 1][0] == H for i in range(world - 1))
+            assert all(r[1] - r[0] <= r[2] for r in rows)
