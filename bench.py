@@ -276,7 +276,7 @@ def run_ours(args):
                 img = full.cpu()
                 d2h = img.numel()
         else:
-            img = fgl.read_plane("ssaa_u8" if info["ssaa"] else "frame_u8")
+            img = fgl.read_plane("ssaa_u8" if info["ssaa"] else "frame_u8", pinned=True)  # page-locked host buffer (fgl_host_alloc)
             d2h = int(img.nbytes)
         t1 = time.perf_counter()
         if i:

@@ -110,6 +110,9 @@ class Fgl:
         L.fgl_write_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.fgl_copy_plane_rows_to_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.fgl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.fgl_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.fgl_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        self._host_bufs = {}
         L.fgl_destroy.argtypes = [C.c_void_p]
         L.fgl_destroy.restype = None
         self._own = ctx is None
@@ -121,7 +124,22 @@ class Fgl:
             ctx = p
         self.ctx = ctx if isinstance(ctx, C.c_void_p) else C.c_void_p(ctx)
 
+    def host_array(self, shape, dtype, key=None):
+        """numpy array on page-locked memory from fgl_host_alloc (cached per key/shape/dtype, reused between calls)."""
+        k = (key, tuple(shape), np.dtype(dtype).str)
+        if k not in self._host_bufs:
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            p = C.c_void_p()
+            self.call("fgl_host_alloc", n, C.byref(p))
+            buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+            self._host_bufs[k] = (p, np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape))
+        return self._host_bufs[k][1]
+
     def close(self):
+        if self.ctx:
+            for p, _ in self._host_bufs.values():
+                self.lib.fgl_host_free(self.ctx, p)
+            self._host_bufs = {}
         if self._own and self.ctx:
             self.lib.fgl_destroy(self.ctx)
         self.ctx = None
@@ -222,13 +240,15 @@ class Fgl:
         self.call("fgl_plane_info", int(plane), C.byref(w), C.byref(h), C.byref(ch), C.byref(b))
         return w.value, h.value, ch.value, b.value
 
-    def read_plane(self, plane):
-        """Returns (H, W) or (H, W, 3) numpy array; float32, uint8 (RGB8 images) or int32 (primitive ids)."""
+    def read_plane(self, plane, pinned=False):
+        """Returns (H, W) or (H, W, 3) numpy array; float32, uint8 (RGB8 images) or int32 (primitive ids).
+        pinned=True reads into a cached page-locked buffer (valid until the next pinned read of the same plane)."""
         if isinstance(plane, str):
             plane = PLANE_NAMES[plane]
         w, h, ch, b = self.plane_info(plane)
         dt = np.uint8 if b == 1 else (np.int32 if plane in (PLANE_PRIMID_CAMERA, PLANE_PRIMID_LIGHT) else np.float32)
-        a = np.empty((h, w, ch) if ch > 1 else (h, w), dtype=dt)
+        shape = (h, w, ch) if ch > 1 else (h, w)
+        a = self.host_array(shape, dt, key=plane) if pinned else np.empty(shape, dtype=dt)
         self.call("fgl_read_plane", int(plane), a.ctypes.data_as(C.c_void_p), a.nbytes)
         return a
 

@@ -72,7 +72,7 @@ bool is1ch(int plane) { return plane == FGL_PLANE_DEPTH || plane == FGL_PLANE_SH
 
 int plane_init(fgl_ctx* c, int plane, int w, int h, float value)
 {
-    if (w <= 0 || h <= 0 || w > 65535 || h > 65535) return fgl_fail(c, FGL_ERR_INVALID, "buffer size out of range");
+    if (w <= 0 || h <= 0 || w > 65535 || h > 65535 || (size_t)w * h > 0x7fffffffull) return fgl_fail(c, FGL_ERR_INVALID, "buffer size out of range");
     PlaneH& p = c->planes[plane];
     p.w = w, p.h = h, p.ch = is1ch(plane) ? 1 : 3;
     if (int rc = fgl_reserve(c, p.buf, (size_t)w * h * p.ch * 4)) return rc;
@@ -761,6 +761,21 @@ int fgl_read_plane(fgl_ctx* c, int plane, void* dst, size_t bytes)
     if (bytes != n) return fgl_fail(c, FGL_ERR_INVALID, "fgl_read_plane: size mismatch (have " + std::to_string(n) + ")");
     if (n) FGL_CUDA(c, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGL_OK;
+}
+
+int fgl_host_alloc(fgl_ctx* c, size_t bytes, void** out)
+{
+    ENTER(c);
+    if (!out) return fgl_fail(c, FGL_ERR_INVALID, "fgl_host_alloc: out is NULL");
+    *out = nullptr;
+    FGL_CUDA(c, cudaHostAlloc(out, std::max<size_t>(bytes, 16), cudaHostAllocDefault));
+    return FGL_OK;
+}
+int fgl_host_free(fgl_ctx* c, void* p)
+{
+    ENTER(c);
+    if (p) FGL_CUDA(c, cudaFreeHost(p));
     return FGL_OK;
 }
 

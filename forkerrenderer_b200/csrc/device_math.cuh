@@ -247,10 +247,12 @@ struct ShadowMapD
 FGL_D float shadow_lookup(const ShadowMapD& sm, float u, float v)
 {
     if (!(u >= 0.f && u <= 1.f && v >= 0.f && v <= 1.f)) return __int_as_float(0x7f800000);  // NaN coordinates would index out of bounds in the reference
-    int   iu = f2i_x86((float)sm.iw * u);
-    int   iv = f2i_x86((float)sm.ih * v);
-    float depth = __ldg(sm.d + (size_t)iu + (size_t)iv * sm.w);
-    return ((double)depth < 0.001) ? 1.f : depth;
+    // u, v are in [0, 1] here, so the products are in [0, iw] x [0, ih]: the plain truncating conversion is the x86 one
+    // (no INT_MIN case), and the texel index fits 32 bits (shadow maps have < 2^31 texels: fgl_init_shadow_buffer)
+    int   iu = (int)((float)sm.iw * u);
+    int   iv = (int)((float)sm.ih * v);
+    float depth = __ldg(sm.d + (iu + iv * sm.w));
+    return (depth < 0.001f) ? 1.f : depth;  // == ((double)depth < 0.001), shadow.cpp:33-34: float(0.001) is the smallest float above 0.001
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -2,6 +2,8 @@
 // (shadow.cpp:23-132) and the 8-bit quantise (buffer.cpp:113-126); SSAO (render.cpp:214-286); the in-place
 // Gaussian blur as the recurrence it is (buffer.cpp:59-98); the SSAA box resolve (render.cpp:291-343); clears and
 // layout conversions for the host accessors.
+#include <cuda_pipeline.h>
+
 #include <cstdlib>
 
 #include "fgl_internal.h"
@@ -221,66 +223,125 @@ __device__ __forceinline__ float blur_step(BlurState& s, float x0, float x1, flo
     return r;
 }
 
-constexpr int kBlurTile = 128;
-// H pass: a CTA owns 32 rows; tiles of 128 columns (+4 look-ahead) are staged in shared memory with coalesced loads,
-// one warp (a lane per row) walks the recurrence, the tile is written back coalesced.
+// Both passes are bound by the recurrence itself: from y[w-1] to y[w] there is one multiply and seven dependent adds
+// (32 cycles; the summation order is part of the result), so a line of n samples costs >= 32 n cycles no matter how
+// wide the machine is.  The kernels therefore keep ONE walking warp per 32 lines fed from shared memory and hide all
+// global traffic behind it: a three-stage ring of tiles, the other seven warps load tile i and store tile i - 2
+// while warp 0 walks tile i - 1 (one __syncthreads per stage).  In-place hazards: a tile's look-ahead (4 samples past
+// its end) is read before the following tile is stored, exactly like the reference's loop reads not yet written data.
+constexpr int kBlurTW = 96, kBlurLD = kBlurTW + 5;  // H: tile width, row pitch (101 = 5 mod 32: conflict-free)
+constexpr int kBlurTR = 64;                         // V: tile rows
+
 __global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H, int rowBegin)
 {
-    __shared__ float tile[32][kBlurTile + 4 + 1];
+    __shared__ float tile[3][32][kBlurLD];
     const int row0 = rowBegin + blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nT = (W + kBlurTW - 1) / kBlurTW;
     BlurState st;
     st.h1 = st.h2 = st.h3 = st.h4 = 0.f;
-    for (int c0 = 0; c0 < W; c0 += kBlurTile)
+    for (int i = 0; i < nT + 2; ++i)
     {
-        int tw = min(kBlurTile, W - c0);
-        for (int r = warp; r < 32; r += 8)
+        if (warp == 0)
         {
-            int row = row0 + r;
-            if (row >= H) continue;
-            for (int j = lane; j < tw + 4; j += 32) tile[r][j] = a[(size_t)row * W + min(c0 + j, W - 1)];
-        }
-        __syncthreads();
-        if (warp == 0 && row0 + lane < H)
-        {
-            if (c0 == 0) st.h1 = st.h2 = st.h3 = st.h4 = tile[lane][0];
-            for (int j = 0; j < tw; ++j)
+            const int k = i - 1;
+            if (k >= 0 && k < nT && row0 + lane < H)
             {
-                float r = blur_step(st, tile[lane][j], tile[lane][j + 1], tile[lane][j + 2], tile[lane][j + 3], tile[lane][j + 4], c0 + j == 0);
-                tile[lane][j] = r;
+                float* t = tile[k % 3][lane];
+                const int c0 = k * kBlurTW, tw = min(kBlurTW, W - c0);
+                if (k == 0) st.h1 = st.h2 = st.h3 = st.h4 = t[0];
+                float x0 = t[0], x1 = t[1], x2 = t[2], x3 = t[3];
+#pragma unroll 8
+                for (int j = 0; j < tw; ++j)
+                {
+                    float x4 = t[j + 4];
+                    float r = blur_step(st, x0, x1, x2, x3, x4, c0 + j == 0);
+                    t[j] = r;
+                    x0 = x1, x1 = x2, x2 = x3, x3 = x4;
+                }
             }
         }
-        __syncthreads();
-        for (int r = warp; r < 32; r += 8)
+        else
         {
-            int row = row0 + r;
-            if (row >= H) continue;
-            for (int j = lane; j < tw; j += 32) a[(size_t)row * W + c0 + j] = tile[r][j];
+            const int ks = i - 2;
+            if (ks >= 0)
+            {
+                const int c0 = ks * kBlurTW, tw = min(kBlurTW, W - c0);
+                for (int r = warp - 1; r < 32; r += 7)
+                {
+                    int row = row0 + r;
+                    if (row >= H) break;
+                    for (int j = lane; j < tw; j += 32) a[(size_t)row * W + c0 + j] = tile[ks % 3][r][j];
+                }
+            }
+            if (i < nT)
+            {   // asynchronous copies (LDGSTS): all of a thread's loads are in flight at once, nothing is staged in registers
+                const int c0 = i * kBlurTW, tw4 = min(kBlurTW, W - c0) + 4;
+                for (int e = threadIdx.x - 32; e < 32 * tw4; e += 224)
+                {
+                    int r = e / tw4, j = e - r * tw4, row = row0 + r;
+                    if (row < H) __pipeline_memcpy_async(&tile[i % 3][r][j], &a[(size_t)row * W + min(c0 + j, W - 1)], 4);
+                }
+                __pipeline_commit();
+            }
+            __pipeline_wait_prior(0);
         }
         __syncthreads();
     }
 }
 
-// V pass: one thread per column, rows walked in order; loads and stores are coalesced across the warp.
-// rowBegin > 0 (sort-first band): the recurrence is warmed up from a row >= 64 above the band; its memory of the
-// start decays as 0.61^n, far below fp32 resolution after 64 rows.
-__global__ void __launch_bounds__(64) k_blur_v(float* a, int W, int H, int rowBegin, int rowEnd)
+// V pass: a CTA owns 32 columns, lane = column.  rowBegin > 0 (sort-first band): the recurrence is warmed up from a
+// row >= 64 above the band; its memory of the start decays as 0.61^n, far below fp32 resolution after 64 rows
+// (DESIGN.md §6).  Look-ahead rows past the bottom edge re-read the not yet overwritten last row, as the in-place
+// loop of the reference does.
+__global__ void __launch_bounds__(256) k_blur_v(float* a, int W, int H, int rowBegin, int rowEnd)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
-    const int b = rowBegin;
-    float     x0 = a[(size_t)b * W + x], x1 = a[(size_t)min(b + 1, H - 1) * W + x], x2 = a[(size_t)min(b + 2, H - 1) * W + x],
-          x3 = a[(size_t)min(b + 3, H - 1) * W + x];
-    BlurState st;
-    st.h1 = st.h2 = st.h3 = st.h4 = x0;
-    for (int h = b; h < rowEnd; ++h)
+    __shared__ float tile[3][kBlurTR + 4][32];
+    const int  warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int  x = blockIdx.x * 32 + lane;
+    const bool colOk = x < W;
+    const int  nT = (rowEnd - rowBegin + kBlurTR - 1) / kBlurTR;
+    BlurState  st;
+    st.h1 = st.h2 = st.h3 = st.h4 = 0.f;
+    for (int i = 0; i < nT + 2; ++i)
     {
-        // a[min(h+4, H-1)] is still original: rows below h have not been written yet (at the bottom edge the
-        // clamped taps re-read the not yet overwritten last row, exactly as the in-place loop does)
-        float x4 = (h + 4 <= H - 1) ? a[(size_t)(h + 4) * W + x] : x3;  // x3 already holds the last row when clamping
-        float r = blur_step(st, x0, x1, x2, x3, x4, h == b);
-        a[(size_t)h * W + x] = r;
-        x0 = x1, x1 = x2, x2 = x3, x3 = x4;
+        if (warp == 0)
+        {
+            const int k = i - 1;
+            if (k >= 0 && k < nT)
+            {
+                float(*t)[32] = tile[k % 3];
+                const int r0 = rowBegin + k * kBlurTR, th = min(kBlurTR, rowEnd - r0);
+                if (k == 0) st.h1 = st.h2 = st.h3 = st.h4 = t[0][lane];
+                float x0 = t[0][lane], x1 = t[1][lane], x2 = t[2][lane], x3 = t[3][lane];
+#pragma unroll 8
+                for (int j = 0; j < th; ++j)
+                {
+                    float x4 = t[j + 4][lane];
+                    float r = blur_step(st, x0, x1, x2, x3, x4, r0 + j == rowBegin);
+                    t[j][lane] = r;
+                    x0 = x1, x1 = x2, x2 = x3, x3 = x4;
+                }
+            }
+        }
+        else
+        {
+            const int ks = i - 2;
+            if (ks >= 0 && colOk)
+            {
+                const int r0 = rowBegin + ks * kBlurTR, th = min(kBlurTR, rowEnd - r0);
+                for (int r = warp - 1; r < th; r += 7) a[(size_t)(r0 + r) * W + x] = tile[ks % 3][r][lane];
+            }
+            if (i < nT)
+            {
+                const int r0 = rowBegin + i * kBlurTR, th = min(kBlurTR, rowEnd - r0);
+                if (colOk)
+                    for (int r = warp - 1; r < th + 4; r += 7) __pipeline_memcpy_async(&tile[i % 3][r][lane], &a[(size_t)min(r0 + r, H - 1) * W + x], 4);
+                __pipeline_commit();
+            }
+            __pipeline_wait_prior(0);
+        }
+        __syncthreads();
     }
 }
 
@@ -412,7 +473,7 @@ int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind,
         }
         {
             LaunchScope ls(c, "blur_v", n * 8);
-            k_blur_v<<<(W + 63) / 64, 64, 0, c->stream>>>(plane + ch * n, W, H, vRow0, vRow1);
+            k_blur_v<<<(W + 31) / 32, 256, 0, c->stream>>>(plane + ch * n, W, H, vRow0, vRow1);
         }
     }
     return check_launch(c, "blur");

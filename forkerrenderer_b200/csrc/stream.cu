@@ -23,6 +23,9 @@
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "stream.h"
 
 namespace
@@ -30,8 +33,7 @@ namespace
 constexpr int    kMT = 624;
 constexpr int    kCB = 256;                      // generator blocks per checkpoint
 constexpr size_t kWindowCand = (size_t)64 << 20;  // candidates per build window
-constexpr int    kT = 2048;                      // uncertain pixels per super-chunk of the PCSS chain
-constexpr int    kWin = 64;                      // candidate offsets evaluated per row, centred on the prediction
+constexpr int    kChainNW = 2;                   // PCSS chain: candidate offsets evaluated per row = 32 * kChainNW, centred on the prediction
 
 __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
 {
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* raw, size_t nCa
 __global__ void k_acc_add(unsigned long long* acc, const int* total) { *acc += (unsigned long long)*total; }
 
 // ---- PCSS chain ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fix_depth(float d) { return ((double)d < 0.001) ? 1.f : d; }  // shadow.cpp:33-34
+// shadow.cpp:33-34 compares (double)d < 0.001; float(0.001) = 0.00100000004749745 is the smallest float above 0.001, so
+// d < 0.001f is the same predicate for every float d
+__device__ __forceinline__ float fix_depth(float d) { return (d < 0.001f) ? 1.f : d; }
 
 // separable box min / max of the fixed-up shadow map over the window [x + lo, x + hi] x [y + lo, y + hi]
 // (lo = -r, hi = r: centred box of the search footprint; lo = 0, hi = bw - 1: box anchored at its first texel)
@@ -338,6 +342,7 @@ struct ChainRows
     const float2*             disk;
     double                    fs;
     unsigned long long        base;  // chunk of site i with k earlier blockers = base + i + 2 k
+    unsigned long long*       stats;  // diagnostics (FGL_CHAIN_STATS=1): pairs, decided-one, ambiguous, taps in E\F cells, warp tasks
 };
 
 // flags of up to 32 (row, chunk) pairs, one per lane: signature tests first, then the warp evaluates the ambiguous
@@ -349,6 +354,25 @@ __device__ __forceinline__ uint32_t eval_pairs(const ChainRows& R, bool valid, i
     bool               one = (sg & F) != 0ull;
     uint32_t           w = __ballot_sync(0xffffffffu, valid && one);
     uint32_t           amb = __ballot_sync(0xffffffffu, valid && !one && (sg & E) != 0ull);
+    if (R.stats)
+    {
+        uint32_t nv = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0)
+        {
+            atomicAdd(R.stats + 0, (unsigned long long)__popc(nv)), atomicAdd(R.stats + 1, (unsigned long long)__popc(w));
+            atomicAdd(R.stats + 2, (unsigned long long)__popc(amb)), atomicAdd(R.stats + 4, 1ull);
+        }
+        for (uint32_t a = amb; a; a &= a - 1)
+        {
+            int                b = __ffs(a) - 1;
+            size_t             cq = __shfl_sync(0xffffffffu, chunk, b);
+            unsigned long long Fq = __shfl_sync(0xffffffffu, F, b), Eq = __shfl_sync(0xffffffffu, E, b);
+            float2             d = __ldg(R.disk + cq * 32 + lane);
+            int                bit = cell_of(d.y) * 8 + cell_of(d.x);
+            uint32_t           hits = __ballot_sync(0xffffffffu, ((Eq & ~Fq) >> bit) & 1ull);
+            if (lane == 0) atomicAdd(R.stats + 3, (unsigned long long)__popc(hits));
+        }
+    }
     while (amb)
     {
         int  b[4];
@@ -395,158 +419,435 @@ __global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot)
     if (valid) pilot[j] = (w >> lane) & 1u;
 }
 
-enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_NBLOCKERS = 8 };
+enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_ARRIVE = 4, CH_EPOCH = 5, CH_ERROR = 6, CH_ARRIVE_ROWS = 7, CH_NBLOCKERS = 8 };
 
-// one warp per (row t of the super-chunk, half of its window): lane = candidate
-__global__ void __launch_bounds__(256) k_chain_eval(ChainRows R, const unsigned* state, const int* Ppre, uint32_t* win, int* winLo)
+// ---- the chain as ONE persistent cooperative kernel ----------------------------------------------------------------
+// A super-chunk is cut into segments of kSeg = 32 rows.  Per iteration (one super-chunk from an exactly known state):
+//   (1) every CTA evaluates whole segments: warp = row, lane = candidate offset of the row's window (signature test,
+//       then the taps of the ambiguous candidates — only the taps that fall into a cell in which a texel can block);
+//   (2) the same CTA turns the 32 x W window bits into the segment's transfer table: for every offset d the segment
+//       can be entered with, the offset it is left with (G8) and the 32 blocker flags on the way (GM).  W threads
+//       walk 32 rows each, out of shared memory;
+//   (3) all CTAs arrive on a counter; CTA 0 composes the segment tables in order (32 warps compose groups of
+//       segments for every entry, one thread chains the groups, the warps re-walk their group from its now known
+//       entry), commits the longest prefix of segments whose windows contained the true offset, publishes the new
+//       state (epoch flag; the other CTAs spin on it) and writes the committed rows' flags while the next iteration
+//       is already being evaluated (tables are double-buffered by iteration parity).
+// Nothing here depends on the prediction being right: a segment entered outside its window ends the super-chunk in
+// front of it, and segment 0 is always valid (its rows' windows start at offset 0 and the offset is < 32).
+constexpr int kSeg = 32;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 {
-    if (state[CH_DONE]) return;
-    int lane = threadIdx.x & 31;
-    int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int t = task >> 1, half = task & 1;
-    int j0 = (int)state[CH_J0], j = j0 + t;
-    if (t >= kT || j >= R.nU) return;
-    unsigned m0 = state[CH_M0];
-    int      dhat = __ldg(Ppre + j) - __ldg(Ppre + j0);
-    int      lo = max(0, dhat - kWin / 2);
-    int      d = lo + 32 * half + lane;
-    bool     valid = d <= t;
-    size_t   chunk = (size_t)R.base + R.Upix[j] + 2 * ((size_t)R.Uc1[j] + m0 + (size_t)d);
-    uint32_t w = eval_pairs(R, valid, j, chunk, lane);
-    if (lane == 0)
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// spins until *p >= want; gives up (returns false) after ~2 s so a broken launch can never hang the device
+__device__ __forceinline__ bool spin_until(const unsigned* p, unsigned want)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_u32(p) < want)
     {
-        win[t * 2 + half] = w;
-        if (half == 0) winLo[t] = lo;
+        __nanosleep(20);
+        if (clock64() - t0 > 4000000000LL) return false;
     }
+    return true;
 }
 
-// One CTA, two rows per thread: finds the rows whose flag depends on the candidate, walks them serially, validates
-// that every row's true offset was inside its window, commits the valid prefix and advances the state.
-__device__ __forceinline__ void classify_row(unsigned long long bits, int first, int last, int& isConst, int& val)
-{   // flag constant over candidate indices [first, last] of the window?  (empty range: treated as dependent)
-    if (first > last)
-    {
-        isConst = 0, val = 0;
-        return;
-    }
-    int                n = last - first + 1;
-    unsigned long long m = (n >= 64 ? ~0ull : ((1ull << n) - 1ull)) << first;
-    bool               all0 = (bits & m) == 0ull, all1 = (bits & m) == m;
-    isConst = all0 || all1, val = all1 ? 1 : 0;
+// position of the k-th (zero-based) set bit of m; m has more than k bits set
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int k)
+{
+    int pos = 0, c;
+    c = __popc(m & 0xffffu);
+    if (k >= c) k -= c, pos += 16, m >>= 16;
+    c = __popc(m & 0xffu);
+    if (k >= c) k -= c, pos += 8, m >>= 8;
+    c = __popc(m & 0xfu);
+    if (k >= c) k -= c, pos += 4, m >>= 4;
+    c = __popc(m & 0x3u);
+    if (k >= c) k -= c, pos += 2, m >>= 2;
+    if (k >= (int)(m & 1u)) pos += 1;
+    return pos;
 }
 
-__global__ void __launch_bounds__(kT / 2) k_chain_walk(int nU, unsigned* state, const uint32_t* win, const int* winLo, uint8_t* flagU)
-{
-    typedef cub::BlockScan<unsigned long long, kT / 2> Scan64;
-    typedef cub::BlockScan<int, kT / 2>                Scan32;
-    __shared__ union
-    {
-        typename Scan64::TempStorage a;
-        typename Scan32::TempStorage b;
-    } tmp;
-    __shared__ unsigned long long bitsS[kT];
-    __shared__ int                offS[kT];  // per candidate-dependent row: constant blockers before it minus its window origin
-    __shared__ short              sensRow[kT];
-    __shared__ short              idxS[kT];
-    __shared__ uint8_t            nvS[kT], flagS[kT];
-    __shared__ int                nSens, tstop, firstBad;
+constexpr int kMaxSpc = 3;                 // segments one CTA evaluates per iteration
+constexpr int kRowsCta = kMaxSpc * kSeg;  // rows of those segments
 
-    if (state[CH_DONE]) return;
-    const int j0 = (int)state[CH_J0];
-    const int nLive = min(kT, nU - j0);
-    if (threadIdx.x == 0) firstBad = kT, tstop = kT;
-    unsigned long long bits[2];
-    int                lo[2], nv[2], isConst[2], val[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
+// Shared memory of k_chain_fused (dynamic; CTA 0 also holds the tables of the whole iteration)
+template <int NW>
+struct ChainSmem
+{
+    static constexpr int W = 32 * NW;
+    static constexpr int kMaxSegs = 148 * kMaxSpc;
+    // evaluation (every CTA)
+    float4             rowS[kRowsCta];    // shadow coordinate + bias of the row
+    unsigned long long rowE[kRowsCta];    // cells in which a tap can block
+    unsigned long long rowChunk0[kRowsCta];
+    uint32_t           bits[kRowsCta][NW];  // window bits: bit l of word h = blocker flag of candidate offset lo + 32 h + l
+    uint32_t           amb[kRowsCta * NW];  // candidates the signature test left undecided
+    int                pre[kRowsCta * NW + 1];
+    int                lo[kRowsCta];
+    uint4              pairQ[32][8];      // per warp: the eight candidates of the current step (chunk lo / hi, work-list word, bit)
+    // composition (CTA 0)
+    uint8_t G[kMaxSegs * W];
+    int     segLo[kMaxSegs], entry[kMaxSegs], after[kMaxSegs];
+    short   GT[32 * W];
+    int     groupD[33];
+    int     ctl[8];
+};
+
+template <int NW>
+__global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* state, const int* Ppre, uint8_t* G8all, uint32_t* GMall, int* segLoAll,
+                                                        uint32_t* rowBits, int* rowLo, uint8_t* flagU, int segsPerIter)
+{
+    constexpr int W = 32 * NW;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    ChainSmem<NW>& S = *reinterpret_cast<ChainSmem<NW>*>(smemRaw);
+    uint8_t* const sG = S.G;
+    int* const     sSegLo = S.segLo;
+    int* const     sEntry = S.entry;
+    int* const     sAfter = S.after;
+    short* const   sGT = S.GT;
+    int* const     sGroupD = S.groupD;
+    int* const     sCtl = S.ctl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (unsigned it = 0;; ++it)
     {
-        int t = threadIdx.x * 2 + k;
-        isConst[k] = 1, val[k] = 0, lo[k] = 0, nv[k] = 1, bits[k] = 0ull;
-        if (t < nLive)
+        if (threadIdx.x == 0)
         {
-            bits[k] = (unsigned long long)win[t * 2] | ((unsigned long long)win[t * 2 + 1] << 32);
-            lo[k] = winLo[t];
-            nv[k] = min(kWin, t - lo[k] + 1);
-            classify_row(bits[k], 0, nv[k] - 1, isConst[k], val[k]);
+            bool ok = true;
+            if (blockIdx.x != 0 && it > 0) ok = spin_until(state + CH_EPOCH, it);
+            sCtl[0] = (int)ld_acquire_u32(state + CH_J0), sCtl[1] = (int)ld_acquire_u32(state + CH_M0);
+            sCtl[2] = ok ? (int)ld_acquire_u32(state + CH_DONE) : 1;
+            if (!ok) atomicExch(state + CH_ERROR, 1u);
         }
-    }
-    // one scan for both prefix counts: low word = rows with a constant blocker, high word = candidate-dependent rows.
-    // Second round: a row's true offset lies in [cp, cp + sp], so its flag only has to be constant over that part of
-    // its window; fewer dependent rows means a shorter serial walk.
-    unsigned long long item[2], pre[2], aggregate;
-    int                cp[2], sp[2];
-    for (int round = 0; round < 2; ++round)
-    {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) item[k] = (unsigned long long)(isConst[k] ? val[k] : 0) | ((unsigned long long)(isConst[k] ? 0 : 1) << 32);
-        Scan64(tmp.a).ExclusiveSum(item, pre, aggregate);
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
+        if (sCtl[2]) return;
+        const int      j0 = sCtl[0];
+        const unsigned m0 = (unsigned)sCtl[1];
+        const int      nLive = min(segsPerIter * kSeg, R.nU - j0);
+        const int      nSeg = (nLive + kSeg - 1) / kSeg;
+        uint8_t*       G8 = G8all + (size_t)(it & 1) * segsPerIter * W;
+        uint32_t*      GM = GMall + (size_t)(it & 1) * segsPerIter * W;
+        int*           segLo = segLoAll + (size_t)(it & 1) * segsPerIter;
+        const int      pre0 = __ldg(Ppre + j0);
+        // Evaluation is balanced over the grid by interleaving ROWS: CTA b takes rows b, b + G, b + 2 G, ... (hard rows
+        // come in runs along shadow edges; whole segments per CTA left most SMs waiting for a few).  Its local row
+        // rr = 32 i + warp is super-chunk row t = (32 i + warp) * G + b.  Tables are per SEGMENT: CTA b builds the tables
+        // of segments b, b + G, ... from the rows' bits in global memory after a grid-wide barrier.
+        const int mySegs = blockIdx.x < nSeg ? (nSeg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        constexpr int myRows = kRowsCta, myWords = kRowsCta * NW;
+
+        // (1a) warp per row (up to kMaxSpc rows per warp, their loads in flight together): signature test of the W candidates
         {
-            cp[k] = (int)(pre[k] & 0xffffffffu), sp[k] = (int)(pre[k] >> 32);
-            int t = threadIdx.x * 2 + k;
-            if (round == 0 && t < nLive && !isConst[k])
-                classify_row(bits[k], max(0, cp[k] - lo[k]), min(nv[k] - 1, cp[k] + sp[k] - lo[k]), isConst[k], val[k]);
-        }
-    }
+            unsigned           upix[kMaxSpc], uc1[kMaxSpc];
+            unsigned long long F[kMaxSpc], E[kMaxSpc];
+            float4             sc[kMaxSpc];
+            int                lo[kMaxSpc], tt[kMaxSpc];
+            bool               rowValid[kMaxSpc];
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-        if (!isConst[k])
+            for (int i = 0; i < kMaxSpc; ++i)
+            {
+                tt[i] = (warp + 32 * i) * (int)gridDim.x + (int)blockIdx.x;
+                rowValid[i] = tt[i] < nLive;
+                upix[i] = uc1[i] = 0u, F[i] = E[i] = 0ull, sc[i] = make_float4(0.f, 0.f, 0.f, 0.f), lo[i] = 0;
+                if (rowValid[i])
+                {
+                    const int j = j0 + tt[i];
+                    lo[i] = __ldg(Ppre + j);
+                    upix[i] = __ldg(R.Upix + j), uc1[i] = __ldg(R.Uc1 + j), F[i] = __ldg(R.UF + j), E[i] = __ldg(R.UE + j), sc[i] = __ldg(R.Usc + j);
+                }
+            }
+            unsigned long long sg[kMaxSpc][NW];
+            size_t             chunk0[kMaxSpc];
+#pragma unroll
+            for (int i = 0; i < kMaxSpc; ++i)
+            {
+                lo[i] = rowValid[i] ? max(0, lo[i] - pre0 - W / 2) : 0;
+                chunk0[i] = (size_t)R.base + upix[i] + 2 * ((size_t)uc1[i] + m0 + (size_t)lo[i]);
+#pragma unroll
+                for (int h = 0; h < NW; ++h)
+                {
+                    int  d = lo[i] + 32 * h + lane;
+                    bool valid = rowValid[i] && d <= tt[i];
+                    sg[i][h] = valid ? __ldg(R.sig + chunk0[i] + 2 * (size_t)(32 * h + lane)) : 0ull;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxSpc; ++i)
+            {
+                const int rr = warp + 32 * i;
+#pragma unroll
+                for (int h = 0; h < NW; ++h)
+                {
+                    bool     one = (sg[i][h] & F[i]) != 0ull;
+                    uint32_t wOne = __ballot_sync(0xffffffffu, one);
+                    uint32_t wAmb = __ballot_sync(0xffffffffu, !one && (sg[i][h] & E[i]) != 0ull);
+                    if (lane == 0) S.bits[rr][h] = wOne, S.amb[rr * NW + h] = wAmb;
+                }
+                if (lane == 0) S.lo[rr] = lo[i], S.rowS[rr] = sc[i], S.rowE[rr] = E[i], S.rowChunk0[rr] = (unsigned long long)chunk0[i];
+            }
+        }
+        __syncthreads();
+        // (1b) work list of the undecided candidates of all rows of this CTA: exclusive prefix of their counts
+        if (warp == 0)
         {
-            int i = sp[k];
-            sensRow[i] = (short)(threadIdx.x * 2 + k), offS[i] = cp[k] - lo[k], bitsS[i] = bits[k], nvS[i] = (uint8_t)nv[k];
-        }
-    if (threadIdx.x == 0) nSens = (int)(aggregate >> 32);
-    __syncthreads();
-    const int n = nSens;
-    if (threadIdx.x == 0)
-    {
-        int ms = 0;
-#pragma unroll 4
-        for (int i = 0; i < n; ++i)
-        {   // the only serial dependency of the whole pass: ms -> bit index -> bit -> ms (range check deferred)
-            int idx = offS[i] + ms;
-            int b = (int)((bitsS[i] >> (idx & 63)) & 1ull);
-            idxS[i] = (short)idx;
-            flagS[i] = (uint8_t)b;
-            ms += b;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        if (idxS[i] < 0 || idxS[i] >= (short)nvS[i]) atomicMin(&tstop, (int)sensRow[i]);  // first row whose offset left its window
-    __syncthreads();
-    // blockers among the candidate-dependent rows before each row, then validation of the constant rows
-    int sb[2], msb[2], msTotal;
+            constexpr int kPer = (kRowsCta * NW + 31) / 32;
+            int           cnt[kPer], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) sb[k] = (!isConst[k] && (threadIdx.x * 2 + k) < tstop) ? (int)flagS[sp[k]] : 0;
-    Scan32(tmp.b).ExclusiveSum(sb, msb, msTotal);
+            for (int k = 0; k < kPer; ++k)
+            {
+                int wi = lane * kPer + k;
+                cnt[k] = wi < myWords ? __popc(S.amb[wi]) : 0;
+                sum += cnt[k];
+            }
+            int incl = sum;
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-    {
-        int t = threadIdx.x * 2 + k;
-        if (t < nLive && t < tstop && isConst[k])
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k)
+            {
+                int wi = lane * kPer + k;
+                if (wi < myWords) S.pre[wi] = run;
+                run += cnt[k];
+            }
+            if (lane == 31) S.pre[myWords] = incl;
+        }
+        __syncthreads();
+        // (1c) the undecided candidates, eight per warp step.  Lanes 0..7 locate one candidate each (word of the work list,
+        // bit inside the word, sample chunk).  Then, lane = tap: which of the candidate's 32 taps fall into a cell of E
+        // (an undecided candidate has no sample in a cell of F; a tap outside E cannot block) — about 5 of 32.  Those taps
+        // of all eight candidates are finally evaluated DENSELY, one tap per lane (the sample comes back from L1).
         {
-            int idx = cp[k] + msb[k] - lo[k];
-            if (idx < 0 || idx >= nv[k]) atomicMin(&firstBad, t);
-        }
-    }
-    __syncthreads();
-    const int valid = min(min(tstop, firstBad), nLive);  // >= 1: row 0 always sits at offset 0 of its window
+            const int total = S.pre[myWords];
+            for (int g0 = warp * 8; g0 < total; g0 += 32 * 8)
+            {
+                const int nq = min(8, total - g0);
+                if (lane < nq)
+                {
+                    const int p = g0 + lane;
+                    int       loI = 0, hiI = myWords;  // pre[loI] <= p < pre[hiI]
+                    while (hiI - loI > 1)
+                    {
+                        int mid = (loI + hiI) >> 1;
+                        if (S.pre[mid] <= p) loI = mid;
+                        else hiI = mid;
+                    }
+                    const int                b = nth_set_bit(S.amb[loI], p - S.pre[loI]);
+                    const unsigned long long chunk = S.rowChunk0[loI / NW] + 2ull * (unsigned)(32 * (loI % NW) + b);
+                    S.pairQ[warp][lane] = make_uint4((unsigned)chunk, (unsigned)(chunk >> 32), (unsigned)loI, (unsigned)b);
+                }
+                __syncwarp();
+                uint32_t hm[8];
+                int      cum[9];
+                cum[0] = 0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-    {
-        int t = threadIdx.x * 2 + k;
-        if (t < valid) flagU[j0 + t] = isConst[k] ? (uint8_t)val[k] : flagS[sp[k]];
-        if (t == valid) state[CH_M0] += (unsigned)(cp[k] + msb[k]);  // blockers among the committed rows
-    }
-    if (threadIdx.x == 0)
-    {
-        if (valid == kT) state[CH_M0] += (unsigned)((int)(aggregate & 0xffffffffu) + msTotal);
-        state[CH_J0] = (unsigned)(j0 + valid);
-        state[CH_ITERS] += 1;
-        if (j0 + valid >= nU) state[CH_DONE] = 1;
+                for (int q = 0; q < 8; ++q)
+                {
+                    hm[q] = 0u;
+                    if (q < nq)
+                    {
+                        const uint4  pq = S.pairQ[warp][q];
+                        const size_t chunk = (size_t)pq.x | ((size_t)pq.y << 32);
+                        const float2 d = __ldg(R.disk + chunk * 32 + lane);
+                        const int    cell = (__float2int_rd(d.y * 4.f) + 4) * 8 + (__float2int_rd(d.x * 4.f) + 4);  // = cell_of(y) * 8 + cell_of(x): scaling by 4 is exact
+                        hm[q] = __ballot_sync(0xffffffffu, (S.rowE[pq.z / NW] >> cell) & 1ull);
+                    }
+                    cum[q + 1] = cum[q] + __popc(hm[q]);
+                }
+                for (int base = 0; base < cum[8]; base += 32)
+                {
+                    const int hi = base + lane;
+                    if (hi < cum[8])
+                    {
+                        int      q = 0, c0 = 0;
+                        uint32_t m = hm[0];
+#pragma unroll
+                        for (int jq = 1; jq < 8; ++jq)
+                            if (cum[jq] <= hi) q = jq, c0 = cum[jq], m = hm[jq];
+                        const int    tap = nth_set_bit(m, hi - c0);
+                        const uint4  pq = S.pairQ[warp][q];
+                        const size_t chunk = (size_t)pq.x | ((size_t)pq.y << 32);
+                        const float2 d = __ldg(R.disk + chunk * 32 + tap);
+                        const float4 sc = S.rowS[pq.z / NW];
+                        const float  ox = (float)((double)d.x * R.fs), oy = (float)((double)d.y * R.fs);
+                        if (sc.z > shadow_lookup(R.sm, sc.x + ox, sc.y + oy) + sc.w) atomicOr(&S.bits[pq.z / NW][pq.z % NW], 1u << pq.w);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // window bits and origins of this CTA's rows -> global, then every CTA waits for all rows of the iteration
+        for (int rr = threadIdx.x; rr < kRowsCta; rr += blockDim.x)
+        {
+            const int t = rr * (int)gridDim.x + (int)blockIdx.x;
+            if (t < nLive)
+            {
+#pragma unroll
+                for (int h = 0; h < NW; ++h) rowBits[(size_t)t * NW + h] = S.bits[rr][h];
+                rowLo[t] = S.lo[rr];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            red_release_add_u32(state + CH_ARRIVE_ROWS, 1u);
+            if (!spin_until(state + CH_ARRIVE_ROWS, gridDim.x * (it + 1))) atomicExch(state + CH_ERROR, 4u), sCtl[2] = 1;
+        }
+        __syncthreads();
+        if (sCtl[2]) return;  // (a timed-out barrier: every CTA gives up by itself)
+        // (2) transfer tables of segments blockIdx.x + si * gridDim.x: their rows come back from L2, W threads per segment walk them
+        for (int e = threadIdx.x; e < mySegs * kSeg; e += blockDim.x)
+        {
+            const int si = e / kSeg, t = (blockIdx.x + si * gridDim.x) * kSeg + (e % kSeg);
+            const bool live = t < nLive;
+#pragma unroll
+            for (int h = 0; h < NW; ++h) S.bits[e][h] = live ? __ldcg(rowBits + (size_t)t * NW + h) : 0u;
+            S.lo[e] = live ? __ldcg(rowLo + t) : 0;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < mySegs * W)
+        {
+            const int si = threadIdx.x / W, c = threadIdx.x % W;
+            const int sgi = blockIdx.x + si * gridDim.x;
+            const int rows = min(kSeg, nLive - sgi * kSeg), d0 = S.lo[si * kSeg] + c;
+            int       d = d0;
+            uint32_t  mask = 0u;
+            bool      ok = true;
+            for (int r = 0; r < rows; ++r)
+            {
+                int idx = d - S.lo[si * kSeg + r];
+                if (idx < 0 || idx >= W || d > sgi * kSeg + r)
+                {
+                    ok = false;
+                    break;
+                }
+                uint32_t bit = (S.bits[si * kSeg + r][idx >> 5] >> (idx & 31)) & 1u;
+                mask |= bit << r, d += (int)bit;
+            }
+            G8[(size_t)sgi * W + c] = ok ? (uint8_t)(d - d0) : (uint8_t)255;
+            GM[(size_t)sgi * W + c] = mask;
+            if (c == 0) segLo[sgi] = S.lo[si * kSeg];
+        }
+        // (3) arrive
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) red_release_add_u32(state + CH_ARRIVE, 1u);
+        if (blockIdx.x != 0) continue;
+
+        if (threadIdx.x == 0)
+        {
+            bool ok = spin_until(state + CH_ARRIVE, gridDim.x * (it + 1));
+            sCtl[3] = ok ? 0 : 1;
+        }
+        __syncthreads();
+        if (sCtl[3])
+        {
+            if (threadIdx.x == 0)
+            {
+                atomicExch(state + CH_ERROR, 2u), atomicExch(state + CH_DONE, 1u);
+                __threadfence();
+                st_release_u32(state + CH_EPOCH, 0x7fffffffu);
+            }
+            return;
+        }
+        for (int i = threadIdx.x; i < nSeg * W / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sG)[i] = __ldcg(reinterpret_cast<const uint32_t*>(G8) + i);
+        for (int i = threadIdx.x; i < nSeg; i += blockDim.x) sSegLo[i] = __ldcg(segLo + i);
+        __syncthreads();
+        // compose: warp g owns segments [g * gs, (g + 1) * gs)
+        const int gs = (nSeg + 31) / 32, sBeg = warp * gs, sEnd = min(nSeg, sBeg + gs);
+        if (sBeg < nSeg)
+        {
+#pragma unroll
+            for (int k = 0; k < NW; ++k)
+            {
+                const int c = lane + 32 * k, d0 = sSegLo[sBeg] + c;
+                int       d = d0;
+                bool      ok = true;
+                for (int sgi = sBeg; sgi < sEnd; ++sgi)
+                {
+                    int cc = d - sSegLo[sgi];
+                    if (cc < 0 || cc >= W)
+                    {
+                        ok = false;
+                        break;
+                    }
+                    unsigned g = sG[sgi * W + cc];
+                    if (g == 255u)
+                    {
+                        ok = false;
+                        break;
+                    }
+                    d += (int)g;
+                }
+                sGT[warp * W + c] = ok ? (short)(d - d0) : (short)-1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {   // chain the groups: entry offset of every group, -1 = not reached
+            int  d = 0;
+            bool alive = true;
+            for (int g = 0; g < 32; ++g)
+            {
+                int first = g * gs;
+                sGroupD[g] = (alive && first < nSeg) ? d : -1;
+                if (!alive || first >= nSeg) continue;
+                int cc = d - sSegLo[first];
+                int v = (cc >= 0 && cc < W) ? (int)sGT[g * W + cc] : -1;
+                if (v < 0) alive = false;  // the first invalid segment lies in this group: its warp finds it below
+                else d += v;
+            }
+            sCtl[4] = nSeg;  // first invalid segment
+        }
+        __syncthreads();
+        if (lane == 0 && sBeg < nSeg && sGroupD[warp] >= 0)
+        {
+            int d = sGroupD[warp];
+            for (int sgi = sBeg; sgi < sEnd; ++sgi)
+            {
+                int      cc = d - sSegLo[sgi];
+                unsigned g = (cc >= 0 && cc < W) ? (unsigned)sG[sgi * W + cc] : 255u;
+                if (g == 255u)
+                {
+                    atomicMin(&sCtl[4], sgi);
+                    break;
+                }
+                sEntry[sgi] = cc, d += (int)g, sAfter[sgi] = d;
+            }
+        }
+        __syncthreads();
+        const int sv = sCtl[4];  // segments [0, sv) are committed
+        const int committed = min(sv * kSeg, nLive);
+        if (threadIdx.x == 0)
+        {
+            if (sv == 0) atomicExch(state + CH_ERROR, 3u), atomicExch(state + CH_DONE, 1u);  // cannot happen (segment 0 is always valid)
+            else
+            {
+                state[CH_J0] = (unsigned)(j0 + committed), state[CH_M0] = m0 + (unsigned)sAfter[sv - 1], state[CH_ITERS] = it + 1;
+                if (j0 + committed >= R.nU) state[CH_DONE] = 1u;
+            }
+            __threadfence();
+            st_release_u32(state + CH_EPOCH, it + 1);
+        }
+        for (int t = threadIdx.x; t < committed; t += blockDim.x)
+        {
+            int sgi = t >> 5;
+            flagU[j0 + t] = (uint8_t)((__ldcg(GM + (size_t)sgi * W + sEntry[sgi]) >> (t & 31)) & 1u);
+        }
+        __syncthreads();
     }
 }
 
@@ -578,11 +879,16 @@ __device__ __forceinline__ float pcf_taps(const ShadowMapD& sm, float4 s, float 
 }
 
 // PCSS visibility of the pixels that have a blocker (shadow.cpp:92-106): persistent warps over the blocker list.
+// The average blocker depth is an ORDERED fp32 sum over the blocking taps (shadow.cpp:78-84): the blocking lanes
+// scatter their depth to shared memory at their rank, every lane then adds the n values in order (broadcast 128-bit
+// reads) — 2-3 instructions per tap instead of a shuffle loop (most pixels with a blocker have all 32 taps blocked).
 __global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
                                                         ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
 {
-    const int      lane = threadIdx.x & 31;
+    __shared__ __align__(16) float sDepth[8][32];
+    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned nb = *nBlockers, nWarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
     for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nWarps)
     {
         unsigned idx = blockerList[i];
@@ -591,16 +897,27 @@ __global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blocker
         float2   d0 = __ldg(disk + first + lane), d1 = __ldg(disk + first + 32 + lane), d2 = __ldg(disk + first + 64 + lane);
         float    ox = (float)((double)d0.x * fs), oy = (float)((double)d0.y * fs);
         float    sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
-        unsigned mask = __ballot_sync(0xffffffffu, s.z > sampleDepth + s.w);
-        float    sum = 0.f, n = 0.f;
-        for (unsigned m = mask; m; m &= m - 1)
-        {   // ordered sum over the blocking taps (shadow.cpp:78-84)
-            sum += __shfl_sync(0xffffffffu, sampleDepth, __ffs(m) - 1);
-            n += 1.f;
+        bool     blocked = s.z > sampleDepth + s.w;
+        unsigned mask = __ballot_sync(0xffffffffu, blocked);
+        const int n = __popc(mask);
+        if (blocked) sDepth[wid][__popc(mask & ltMask)] = sampleDepth;
+        __syncwarp();
+        float sum = 0.f;
+        const float4* q = reinterpret_cast<const float4*>(sDepth[wid]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            if (4 * k >= n) break;
+            float4 v = q[k];
+            sum += v.x;
+            if (4 * k + 1 < n) sum += v.y;
+            if (4 * k + 2 < n) sum += v.z;
+            if (4 * k + 3 < n) sum += v.w;
         }
-        float dBlocker = mask ? sum / n : 0.f;
+        __syncwarp();
+        float dBlocker = mask ? sum / (float)n : 0.f;
         float v = 1.f;
-        if (!((double)dBlocker < 0.001))
+        if (!(dBlocker < 0.001f))  // (double)dBlocker < 0.001 (shadow.cpp:101): float(0.001) is the smallest float above 0.001
         {
             float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
             v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
@@ -637,9 +954,9 @@ struct SampleStream
     unsigned long long ssaoSamples = 0;
     // chain scratch
     DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
-    DevBuf sig, vis, blockerList, pilot, Ppre, winLo;
+    DevBuf sig, vis, blockerList, pilot, Ppre, winLo, chainStats, rowBits;
     unsigned long long sigChunks = 0;
-    unsigned long long chainBlockersBefore = 0;
+    unsigned long long chainTotal = 0;  // blockers found up to and including this context's band
     bool               chainCountValid = false;
 };
 
@@ -654,7 +971,7 @@ void fgl_stream_destroy(fgl_ctx* c)
     SampleStream* s = c->stream_state;
     if (!s) return;
     DevBuf* all[] = { &s->ckpt, &s->window, &s->tileCounts, &s->tileOffsets, &s->counters, &s->ball, &s->disk, &s->smTmpMin, &s->smTmpMax, &s->smMin,
-                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->pilot, &s->Ppre, &s->winLo, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
+                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->pilot, &s->Ppre, &s->winLo, &s->chainStats, &s->rowBits, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
                       &s->chunkOf, &s->mState };
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
@@ -853,11 +1170,14 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         k_classify<<<nb, 256, 0, st>>>(P, n, sc4In, (int*)s->isU.p, (int*)s->isC1.p);
     }
     FGL_CUDA(c, cudaMemsetAsync((int*)s->isU.p + n, 0, 4, st));
+    FGL_CUDA(c, cudaMemsetAsync((int*)s->isC1.p + n, 0, 4, st));
     if (int rc = scan_ints(c, (const int*)s->isU.p, (int*)s->posU.p, n + 1)) return rc;
-    if (int rc = scan_ints(c, (const int*)s->isC1.p, (int*)s->c1pre.p, n)) return rc;
-    int nU = 0;
+    if (int rc = scan_ints(c, (const int*)s->isC1.p, (int*)s->c1pre.p, n + 1)) return rc;
+    int nU = 0, nC1 = 0;  // uncertain sites; sites whose every tap blocks
     FGL_CUDA(c, cudaMemcpyAsync(&nU, (int*)s->posU.p + n, 4, cudaMemcpyDeviceToHost, st));
+    FGL_CUDA(c, cudaMemcpyAsync(&nC1, (int*)s->c1pre.p + n, 4, cudaMemcpyDeviceToHost, st));
     FGL_CUDA(c, cudaStreamSynchronize(st));
+    unsigned long long uncertainBlockers = 0;
     if (int rc = fgl_reserve(c, s->Upix, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Uc1, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Usc, (size_t)(nU + 1) * 16)) return rc;
@@ -884,39 +1204,67 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
         R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p, R.sig = (const unsigned long long*)s->sig.p;
         R.sm = L.sm, R.disk = L.disk, R.fs = L.pcssFilter, R.base = chunkBase;
+        static const bool wantStats = getenv("FGL_CHAIN_STATS") != nullptr;
+        R.stats = nullptr;
+        if (wantStats)
+        {
+            if (int rc = fgl_reserve(c, s->chainStats, 128)) return rc;
+            FGL_CUDA(c, cudaMemsetAsync(s->chainStats.p, 0, 128, st));
+            R.stats = (unsigned long long*)s->chainStats.p;
+        }
         if (int rc = fgl_reserve(c, s->pilot, (size_t)(nU + 1) * 4)) return rc;
         if (int rc = fgl_reserve(c, s->Ppre, (size_t)(nU + 1) * 4)) return rc;
-        if (int rc = fgl_reserve(c, s->bits, (size_t)kT * 2 * 4)) return rc;
-        if (int rc = fgl_reserve(c, s->winLo, (size_t)kT * 4)) return rc;
         {
             LaunchScope ls(c, "pcss_chain_pilot", (uint64_t)nU * 48);
             k_chain_pilot<<<(nU + 255) / 256, 256, 0, st>>>(R, (int*)s->pilot.p);
         }
         FGL_CUDA(c, cudaMemsetAsync((int*)s->pilot.p + nU, 0, 4, st));
         if (int rc = scan_ints(c, (const int*)s->pilot.p, (int*)s->Ppre.p, (size_t)nU + 1)) return rc;
-        int launched = 0;
-        for (;;)
         {
-            int batch = launched == 0 ? (nU + kT - 1) / kT + (nU + kT - 1) / kT / 4 + 2 : 8;
-            for (int it = 0; it < batch; ++it)
+            // persistent cooperative kernel: one CTA per SM, all co-resident (the launch fails otherwise)
+            static int nSM = 0, segsEnv = getenv("FGL_CHAIN_SEGS") ? atoi(getenv("FGL_CHAIN_SEGS")) : 0;
+            const size_t smemBytes = sizeof(ChainSmem<kChainNW>);
+            if (!nSM)
             {
-                {
-                    LaunchScope ls(c, "pcss_chain_eval", 0);
-                    k_chain_eval<<<(kT * 2 * 32 + 255) / 256, 256, 0, st>>>(R, (const unsigned*)s->mState.p, (const int*)s->Ppre.p, (uint32_t*)s->bits.p,
-                                                                          (int*)s->winLo.p);
-                }
-                {
-                    LaunchScope ls(c, "pcss_chain_walk", 0);
-                    k_chain_walk<<<1, kT / 2, 0, st>>>(nU, (unsigned*)s->mState.p, (const uint32_t*)s->bits.p, (const int*)s->winLo.p, (uint8_t*)s->flagU.p);
-                }
+                int perSM = 0;
+                FGL_CUDA(c, cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, c->device));
+                FGL_CUDA(c, cudaFuncSetAttribute(k_chain_fused<kChainNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+                FGL_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_chain_fused<kChainNW>, 1024, smemBytes));
+                if (perSM < 1) return fgl_fail(c, FGL_ERR_CUDA, "pcss chain: the persistent kernel does not fit an SM");
             }
-            launched += batch;
-            unsigned hs[4];
-            FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 16, cudaMemcpyDeviceToHost, st));
+            int grid = std::min(nSM, 148);
+            int segsPerIter = segsEnv > 0 ? segsEnv : kMaxSpc * grid;
+            segsPerIter = std::max(1, std::min(segsPerIter, kMaxSpc * grid));
+            const size_t tw = (size_t)segsPerIter * 32 * kChainNW;
+            if (int rc = fgl_reserve(c, s->bits, 2 * tw * 5)) return rc;  // G8 (1 byte) + GM (4 bytes) per table entry, two parities
+            if (int rc = fgl_reserve(c, s->winLo, 2 * (size_t)segsPerIter * 4)) return rc;
+            uint8_t*       G8 = (uint8_t*)s->bits.p + 2 * tw * 4;
+            uint32_t*      GM = (uint32_t*)s->bits.p;
+            int*           segLo = (int*)s->winLo.p;
+            unsigned*      state = (unsigned*)s->mState.p;
+            const int*     Ppre = (const int*)s->Ppre.p;
+            uint8_t*       flagU = (uint8_t*)s->flagU.p;
+            const size_t   nRows = (size_t)segsPerIter * 32;
+            if (int rc = fgl_reserve(c, s->rowBits, nRows * kChainNW * 4 + nRows * 4)) return rc;
+            uint32_t*      rowBits = (uint32_t*)s->rowBits.p;
+            int*           rowLo = (int*)(rowBits + nRows * kChainNW);
+            void*          args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter };
+            LaunchScope    ls(c, "pcss_chain", 0);
+            FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_chain_fused<kChainNW>, dim3(grid), dim3(1024), args, smemBytes, st));
+        }
+        unsigned hs[8];
+        FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 32, cudaMemcpyDeviceToHost, st));
+        FGL_CUDA(c, cudaStreamSynchronize(st));
+        c->lastChainIters = (int)hs[CH_ITERS];
+        uncertainBlockers = hs[CH_M0];
+        if (hs[CH_ERROR] || !hs[CH_DONE]) return fgl_fail(c, FGL_ERR_STATE, "PCSS chain: persistent kernel failed (code " + std::to_string(hs[CH_ERROR]) + ")");
+        if (R.stats)
+        {
+            unsigned long long hq[16];
+            FGL_CUDA(c, cudaMemcpyAsync(hq, R.stats, 128, cudaMemcpyDeviceToHost, st));
             FGL_CUDA(c, cudaStreamSynchronize(st));
-            c->lastChainIters = (int)hs[CH_ITERS];
-            if (hs[CH_DONE]) break;
-            if (launched > 4 * ((nU + kT - 1) / kT) + 4096) return fgl_fail(c, FGL_ERR_STATE, "PCSS chain did not converge");
+            fprintf(stderr, "[chain stats] sites=%zu uncertain=%d iters=%d | pilot pairs=%llu one=%llu ambiguous=%llu taps_in_E=%llu\n", n, nU, c->lastChainIters,
+                    hq[0], hq[1], hq[2], hq[3]);
         }
     }
     {
@@ -935,7 +1283,9 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
                                                    chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, visB);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
-    s->chainBlockersBefore = blockersBefore, s->chainCountValid = true;
+    // known on the host as soon as the chain kernel has finished — a sort-first driver can hand it to the next band while
+    // this band's filter and lighting kernels are still running
+    s->chainTotal = blockersBefore + (unsigned long long)nC1 + uncertainBlockers, s->chainCountValid = true;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("pcss chain: ") + cudaGetErrorString(e));
     return FGL_OK;
@@ -964,14 +1314,11 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, lo, hi, c->chainBlockersBefore);
 }
 
-// Blockers found up to and including this context's band (= input of the next band's chain); blocks on the stream.
+// Blockers found up to and including this context's band (= input of the next band's chain).  Does not touch the stream.
 int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out)
 {
     SampleStream* s = S_of(c);
-    if (!s->chainCountValid || !s->mState.p) return fgl_fail(c, FGL_ERR_STATE, "no PCSS chain has run on this context");
-    unsigned nb = 0;
-    FGL_CUDA(c, cudaMemcpyAsync(&nb, (unsigned*)s->mState.p + CH_NBLOCKERS, 4, cudaMemcpyDeviceToHost, c->stream));
-    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
-    *out = s->chainBlockersBefore + nb;
+    if (!s->chainCountValid) return fgl_fail(c, FGL_ERR_STATE, "no PCSS chain has run on this context");
+    *out = s->chainTotal;
     return FGL_OK;
 }

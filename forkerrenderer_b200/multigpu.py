@@ -67,20 +67,29 @@ def render_frame(r, rank, world, comm=None, band_out=None):
 
 
 class TorchComm:
-    """send / recv of one integer between ranks with torch.distributed (NCCL on the GPU box, gloo in the CPU tests)."""
+    """send / recv of one integer between ranks with torch.distributed (NCCL on the GPU box, gloo in the CPU tests).
+    On CUDA the transfers run on their own stream: the chain total is known on the host while the band's filter and
+    lighting kernels are still queued on the render stream, and must not wait behind them."""
 
     def __init__(self, dist, device):
         import torch
         self.dist, self.torch, self.device = dist, torch, device
+        self.stream = torch.cuda.Stream(device=device) if getattr(device, "type", "cpu") == "cuda" else None
+
+    def _ctx(self):
+        import contextlib
+        return self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def send_int(self, value, dst):
-        t = self.torch.tensor([int(value)], dtype=self.torch.int64, device=self.device)
-        self.dist.send(t, dst)
+        with self._ctx():
+            t = self.torch.tensor([int(value)], dtype=self.torch.int64, device=self.device)
+            self.dist.send(t, dst)
 
     def recv_int(self, src):
-        t = self.torch.zeros(1, dtype=self.torch.int64, device=self.device)
-        self.dist.recv(t, src)
-        return int(t.item())
+        with self._ctx():
+            t = self.torch.zeros(1, dtype=self.torch.int64, device=self.device)
+            self.dist.recv(t, src)
+            return int(t.item())
 
 
 def gather_bands(dist, torch, band_tensor, height, width, world):

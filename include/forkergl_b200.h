@@ -208,6 +208,11 @@ int fgl_plane_info(fgl_ctx* ctx, int plane, int* out_width, int* out_height, int
 /* Blocking copy to / from HOST memory in the reference's layout (AoS for 3-channel planes). */
 int fgl_read_plane(fgl_ctx* ctx, int plane, void* dst_host, size_t dst_bytes);
 int fgl_write_plane(fgl_ctx* ctx, int plane, const void* src_host, size_t src_bytes);
+/* Page-locked host memory for fgl_read_plane / fgl_write_plane: a read into it is one DMA at PCIe speed instead of a
+ * staged copy into pageable memory (the reference's Buffer::GetValue loops have no counterpart; this is the boundary
+ * a caller reads finished frames through).  Plain malloc/free semantics; the ctx only selects the device. */
+int fgl_host_alloc(fgl_ctx* ctx, size_t bytes, void** out_ptr);
+int fgl_host_free(fgl_ctx* ctx, void* ptr);
 /* Same, but dst is DEVICE memory on the ctx's GPU (e.g. a torch tensor's data_ptr) and the copy is enqueued
  * on the ctx's stream.  Rows [row_begin,row_end) only; used by the multi-GPU gather. */
 int fgl_copy_plane_rows_to_device(fgl_ctx* ctx, int plane, int row_begin, int row_end, void* dst_device,

@@ -1109,6 +1109,8 @@ int fgl_enable_timing(fgl_ctx*, int) { return FGL_OK; }
 int fgl_reset_timings(fgl_ctx*) { return FGL_OK; }
 int fgl_get_timings(fgl_ctx*, FglTiming*, int, int* n) { if (n) *n = 0; return FGL_OK; }
 int fgl_launch_count(fgl_ctx*, uint64_t* o) { if (o) *o = 0; return FGL_OK; }
+int fgl_host_alloc(fgl_ctx*, size_t bytes, void** out) { if (!out) return FGL_ERR_INVALID; *out = malloc(bytes ? bytes : 16); return *out ? FGL_OK : FGL_ERR_INVALID; }
+int fgl_host_free(fgl_ctx*, void* p) { free(p); return FGL_OK; }
 
 // oracle-only: number of mt19937 draws consumed since fgl_begin_frame (used by the stream-accounting tests)
 uint64_t orc_rng_draws(fgl_ctx* c) { return c->draws; }
