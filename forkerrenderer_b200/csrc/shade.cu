@@ -346,16 +346,25 @@ __global__ void __launch_bounds__(256) k_blur_v(float* a, int W, int H, int rowB
 }
 
 // ---- SSAO, one warp per pixel: lane = hemisphere sample (render.cpp:229-285) -----------------------------------------
+// The kernel is bound by instruction issue (profiles/), so the arithmetic that cannot change the result is trimmed:
+//  * VIEWPORT_AFFINE: ForkerGL::SetViewportMatrix (forkergl.cpp:89-102) only fills [0][0], [0][3], [1][1], [1][3], [2][2],
+//    [2][3]; with finite x, y, z the reference's row products ((0 + m0 x) + m1 y) + m2 z) + m3 w reduce to
+//    (0 + m_k v_k) + m3 w bit for bit (adding 0 * finite = +-0 to a sum that is +0 or non-zero changes nothing), and
+//    the w row is never used.  Non-finite coordinates take the general product.
+//  * float -> int: cvttss2si only differs from a plain truncation outside +-2^31 (INT_MIN), checked once per sample.
+template <bool VIEWPORT_AFFINE>
 __global__ void __launch_bounds__(256) k_ssao(SsaoPass S)
 {
-    const size_t n = (size_t)S.W * S.H;
-    const int    lane = threadIdx.x & 31;
-    size_t       idx = (size_t)S.row0 * S.W + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (idx >= (size_t)S.row1 * S.W) return;
-    V3    pos = ld3s(S.worldpos, n, idx), nrm = ld3s(S.normal, n, idx);
-    float fragDepth = S.depth[idx];
+    const unsigned n = (unsigned)S.W * (unsigned)S.H;  // planes have < 2^31 pixels (plane_init)
+    const int      lane = threadIdx.x & 31;
+    const unsigned idx = (unsigned)S.row0 * (unsigned)S.W + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    if (idx >= (unsigned)S.row1 * (unsigned)S.W) return;
+    const float* wp = S.worldpos + idx;
+    const float* np = S.normal + idx;
+    V3           pos = v3(wp[0], wp[n], wp[2 * (size_t)n]), nrm = v3(np[0], np[n], np[2 * (size_t)n]);
+    float        fragDepth = S.depth[idx];
     // accepted unit-ball sample number 32 * pixel + lane of the replayed stream (geometry.h:957-966)
-    const float* b = S.ball + (idx * 32 + lane) * 3;
+    const float* b = S.ball + ((size_t)idx * 32 + lane) * 3;
     V3           v = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
     if (!(vdot(v, nrm) > 0.f)) v = v3(-v.x, -v.y, -v.z);  // geometry.h:978-990
     float sc = vlength(v);
@@ -364,16 +373,29 @@ __global__ void __launch_bounds__(256) k_ssao(SsaoPass S)
     V3 sp = vadd(pos, vscale(v, S.radius));
     V4 sp4;
     sp4.x = sp.x, sp4.y = sp.y, sp4.z = sp.z, sp4.w = 1.f;
-    V4        cs = mat4mul(S.viewProj, sp4);
-    V4        ndc = vdivs4(cs, cs.w);
-    V4        ss = mat4mul(S.viewport, ndc);
-    int       sx = f2i_x86(ss.x), sy = f2i_x86(ss.y);
+    V4 cs = mat4mul(S.viewProj, sp4);
+    V4 ndc = vdivs4(cs, cs.w);
+    float ssx, ssy, ssz;
+    if (VIEWPORT_AFFINE && fabsf(ndc.x) < __int_as_float(0x7f800000) && fabsf(ndc.y) < __int_as_float(0x7f800000) && fabsf(ndc.z) < __int_as_float(0x7f800000))
+    {
+        ssx = (0.f + S.viewport[0] * ndc.x) + S.viewport[3] * ndc.w;
+        ssy = (0.f + S.viewport[5] * ndc.y) + S.viewport[7] * ndc.w;
+        ssz = (0.f + S.viewport[10] * ndc.z) + S.viewport[11] * ndc.w;
+    }
+    else
+    {
+        V4 ss = mat4mul(S.viewport, ndc);
+        ssx = ss.x, ssy = ss.y, ssz = ss.z;
+    }
+    int sx, sy;
+    if (fabsf(ssx) < 1.0e9f && fabsf(ssy) < 1.0e9f) sx = (int)ssx, sy = (int)ssy;
+    else sx = f2i_x86(ssx), sy = f2i_x86(ssy);
     long long li = (long long)sx + (long long)sy * S.W;  // unchecked linear index in the reference (buffer.h:37)
     bool      occ = false;
     if (li >= 0 && li < (long long)n)
     {
         float cached = __ldg(S.depth + li);
-        if (ss.z >= cached + S.bias) occ = S.rangeCheck ? (fabsf(fragDepth - cached) < S.rangeCheckRadius) : true;
+        if (ssz >= cached + S.bias) occ = S.rangeCheck ? (fabsf(fragDepth - cached) < S.rangeCheckRadius) : true;
     }
     int cnt = __popc(__ballot_sync(0xffffffffu, occ));
     if (lane == 0)
@@ -483,7 +505,10 @@ int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S)
 {
     size_t      nPix = (size_t)S.W * (S.row1 - S.row0);
     LaunchScope ls(c, "ssao", nPix * (32 + 384));
-    k_ssao<<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(S);
+    const float* m = S.viewport;  // ForkerGL::SetViewportMatrix structure (rows 0-2; the w row is not used by SSAO)
+    const bool   affine = m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f;
+    if (affine) k_ssao<true><<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(S);
+    else k_ssao<false><<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(S);
     return check_launch(c, "ssao");
 }
 

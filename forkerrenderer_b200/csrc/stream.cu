@@ -145,13 +145,105 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* raw, size_t nCa
 __global__ void k_acc_add(unsigned long long* acc, const int* total) { *acc += (unsigned long long)*total; }
 
 // ---- PCSS chain ----------------------------------------------------------------------------------------------------
+
 // shadow.cpp:33-34 compares (double)d < 0.001; float(0.001) = 0.00100000004749745 is the smallest float above 0.001, so
 // d < 0.001f is the same predicate for every float d
 __device__ __forceinline__ float fix_depth(float d) { return (d < 0.001f) ? 1.f : d; }
 
 // separable box min / max of the fixed-up shadow map over the window [x + lo, x + hi] x [y + lo, y + hi]
-// (lo = -r, hi = r: centred box of the search footprint; lo = 0, hi = bw - 1: box anchored at its first texel)
-__global__ void k_minmax_h(const float* sm, int W, int H, int lo, int hi, float* omin, float* omax)
+// (lo = -r, hi = r: centred box of the search footprint; lo = 0, hi = bw - 1: box anchored at its first texel).
+// Each 1-D pass is a log-step filter in shared memory: m_k[i] = min(a[i .. i + 2^k - 1]) by doubling, and a window of
+// w = hi - lo + 1 samples is the min of two overlapping m_K windows, K = floor(log2 w) — K + 1 operations per sample
+// instead of w.  Samples outside the map are +inf / -inf, i.e. left out, as a clamped loop would.
+constexpr int kMMW = 768;   // H pass: outputs per CTA (one row); window <= 257
+constexpr int kMMR = 128;   // V pass: output rows per CTA (32 columns); window <= 129
+
+__device__ __forceinline__ float2 mm2(float2 a, float2 b) { return make_float2(fminf(a.x, b.x), fmaxf(a.y, b.y)); }
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_minmax_h(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
+{
+    __shared__ float2 t[kMMW + 256];
+    const int   y = blockIdx.y, x0 = blockIdx.x * kMMW, w = hi - lo + 1, nOut = min(kMMW, W - x0), n = nOut + w - 1;
+    const float inf = __int_as_float(0x7f800000);
+    for (int e = threadIdx.x; e < n; e += 256)
+    {
+        int    gx = x0 + lo + e;
+        float2 v = make_float2(inf, -inf);
+        if (gx >= 0 && gx < W)
+        {
+            if (FIRST)
+            {
+                float d = fix_depth(__ldg(imin + (size_t)y * W + gx));
+                v = make_float2(d, d);
+            }
+            else v = make_float2(__ldg(imin + (size_t)y * W + gx), __ldg(imax + (size_t)y * W + gx));
+        }
+        t[e] = v;
+    }
+    __syncthreads();
+    const int K = 31 - __clz(w);
+    for (int k = 0; k < K; ++k)
+    {
+        const int step = 1 << k;
+        float2    v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            int e = threadIdx.x + 256 * q;
+            if (e < n) v[q] = e + step < n ? mm2(t[e], t[e + step]) : t[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            int e = threadIdx.x + 256 * q;
+            if (e < n) t[e] = v[q];
+        }
+        __syncthreads();
+    }
+    for (int o = threadIdx.x; o < nOut; o += 256)
+    {
+        float2 r = mm2(t[o], t[o + w - (1 << K)]);
+        omin[(size_t)y * W + x0 + o] = r.x, omax[(size_t)y * W + x0 + o] = r.y;
+    }
+}
+
+// V pass: 32 columns x kMMR output rows per CTA, ping-pong tiles in dynamic shared memory (2 x 256 x 32 float2 = 128 KB)
+__global__ void __launch_bounds__(512) k_minmax_v(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
+{
+    extern __shared__ __align__(16) unsigned char mmRaw[];
+    float2(*t)[256][32] = reinterpret_cast<float2(*)[256][32]>(mmRaw);
+    const int   lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 16 warps
+    const int   x = blockIdx.x * 32 + lane, y0 = blockIdx.y * kMMR, w = hi - lo + 1, nOut = min(kMMR, H - y0), n = nOut + w - 1;
+    const float inf = __int_as_float(0x7f800000);
+    for (int e = wid; e < n; e += 16)
+    {
+        int    gy = y0 + lo + e;
+        float2 v = make_float2(inf, -inf);
+        if (gy >= 0 && gy < H && x < W) v = make_float2(__ldg(imin + (size_t)gy * W + x), __ldg(imax + (size_t)gy * W + x));
+        t[0][e][lane] = v;
+    }
+    __syncthreads();
+    const int K = 31 - __clz(w);
+    int       cur = 0;
+    for (int k = 0; k < K; ++k)
+    {
+        const int step = 1 << k;
+        for (int e = wid; e < n; e += 16) t[cur ^ 1][e][lane] = e + step < n ? mm2(t[cur][e][lane], t[cur][e + step][lane]) : t[cur][e][lane];
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (x < W)
+        for (int o = wid; o < nOut; o += 16)
+        {
+            float2 r = mm2(t[cur][o][lane], t[cur][o + w - (1 << K)][lane]);
+            omin[(size_t)(y0 + o) * W + x] = r.x, omax[(size_t)(y0 + o) * W + x] = r.y;
+        }
+}
+
+// plain loops, for windows wider than the tiles above are sized for
+__global__ void k_minmax_h_wide(const float* sm, int W, int H, int lo, int hi, float* omin, float* omax)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
@@ -163,7 +255,7 @@ __global__ void k_minmax_h(const float* sm, int W, int H, int lo, int hi, float*
     }
     omin[(size_t)y * W + x] = mn, omax[(size_t)y * W + x] = mx;
 }
-__global__ void k_minmax_v(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
+__global__ void k_minmax_v_wide(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
@@ -1156,11 +1248,30 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     int bw = (int)ceil(0.25 * (double)L.sm.iw * (double)fsF) + 2;
     {
         LaunchScope ls(c, "pcss_minmax", smN * 48);
-        dim3        grid((L.sm.w + 127) / 128, L.sm.h);
-        k_minmax_h<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, -r, r, (float*)s->smTmpMin.p, (float*)s->smTmpMax.p);
-        k_minmax_v<<<grid, 128, 0, st>>>((const float*)s->smTmpMin.p, (const float*)s->smTmpMax.p, L.sm.w, L.sm.h, -r, r, (float*)s->smMin.p, (float*)s->smMax.p);
-        k_minmax_h<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, 0, bw - 1, (float*)s->smTmpMin.p, (float*)s->smTmpMax.p);
-        k_minmax_v<<<grid, 128, 0, st>>>((const float*)s->smTmpMin.p, (const float*)s->smTmpMax.p, L.sm.w, L.sm.h, 0, bw - 1, (float*)s->boxMin.p, (float*)s->boxMax.p);
+        auto box = [&](int lo, int hi, float* omin, float* omax) -> int {
+            const int w = hi - lo + 1;
+            float *   tmin = (float*)s->smTmpMin.p, *tmax = (float*)s->smTmpMax.p;
+            if (w <= 129)
+            {
+                static bool attr = false;
+                if (!attr)
+                {
+                    FGL_CUDA(c, cudaFuncSetAttribute(k_minmax_v, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 32 * 8));
+                    attr = true;
+                }
+                k_minmax_h<true><<<dim3((L.sm.w + kMMW - 1) / kMMW, L.sm.h), 256, 0, st>>>(L.sm.d, nullptr, L.sm.w, L.sm.h, lo, hi, tmin, tmax);
+                k_minmax_v<<<dim3((L.sm.w + 31) / 32, (L.sm.h + kMMR - 1) / kMMR), 512, 2 * 256 * 32 * 8, st>>>(tmin, tmax, L.sm.w, L.sm.h, lo, hi, omin, omax);
+            }
+            else
+            {
+                dim3 grid((L.sm.w + 127) / 128, L.sm.h);
+                k_minmax_h_wide<<<grid, 128, 0, st>>>(L.sm.d, L.sm.w, L.sm.h, lo, hi, tmin, tmax);
+                k_minmax_v_wide<<<grid, 128, 0, st>>>(tmin, tmax, L.sm.w, L.sm.h, lo, hi, omin, omax);
+            }
+            return FGL_OK;
+        };
+        if (int rc = box(-r, r, (float*)s->smMin.p, (float*)s->smMax.p)) return rc;
+        if (int rc = box(0, bw - 1, (float*)s->boxMin.p, (float*)s->boxMax.p)) return rc;
         c->launches += 3;
     }
     P.smMin = (const float*)s->smMin.p, P.smMax = (const float*)s->smMax.p, P.r = r, P.fsF = fsF;
