@@ -327,8 +327,13 @@ def run_ours(args):
     bytes_launch = top["algorithmic_bytes"] / top["launches"]
     achieved = bytes_launch / t_launch / 1e9
     total_kernel_ms = max(1e-9, sum(k["ms_per_frame"] for k in kern))
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu capture of the same workload (null if there is none)
+        traffic = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_traffic.json"))).get(args.workload, {}).get(top["name"])
+    except Exception:
+        pass
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
                 "avg_launch_ms": t_launch * 1e3, "share_of_frame": top["ms_per_frame"] / total_kernel_ms,
                 "note": "largest bandwidth-bound kernel; the per-kernel table is in `kernels` (kernels without a byte figure are latency/ALU bound)"}
 
