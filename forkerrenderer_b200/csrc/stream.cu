@@ -209,13 +209,16 @@ __global__ void __launch_bounds__(256) k_minmax_h(const float* imin, const float
     }
 }
 
-// V pass: 32 columns x kMMR output rows per CTA, ping-pong tiles in dynamic shared memory (2 x 256 x 32 float2 = 128 KB)
+// V pass: 32 columns x kMMR output rows per CTA, ping-pong tiles in dynamic shared memory (2 x (kMMR + w - 1) x 32 float2 <= 128 KB)
 __global__ void __launch_bounds__(512) k_minmax_v(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
 {
     extern __shared__ __align__(16) unsigned char mmRaw[];
-    float2(*t)[256][32] = reinterpret_cast<float2(*)[256][32]>(mmRaw);
     const int   lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 16 warps
     const int   x = blockIdx.x * 32 + lane, y0 = blockIdx.y * kMMR, w = hi - lo + 1, nOut = min(kMMR, H - y0), n = nOut + w - 1;
+    // two tiles of (kMMR + w - 1) rows x 32 columns (the launch sizes the allocation to the window, so two CTAs share an SM)
+    float2(*t0)[32] = reinterpret_cast<float2(*)[32]>(mmRaw);
+    float2(*t1)[32] = t0 + (kMMR + w - 1);
+    float2(*t[2])[32] = { t0, t1 };
     const float inf = __int_as_float(0x7f800000);
     for (int e = wid; e < n; e += 16)
     {
@@ -740,34 +743,48 @@ __global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* 
                     S.pairQ[warp][lane] = make_uint4((unsigned)chunk, (unsigned)(chunk >> 32), (unsigned)loI, (unsigned)b);
                 }
                 __syncwarp();
+                // which taps fall into a cell of E: 8 lanes per candidate, 4 taps (two 16-byte loads) per lane, 4 candidates per
+                // step.  Word 4 st + j, bit 8 a + t  <->  candidate 4 st + a, tap 4 t + j.
                 uint32_t hm[8];
                 int      cum[9];
                 cum[0] = 0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
+                for (int st = 0; st < 2; ++st)
                 {
-                    hm[q] = 0u;
+                    const int q = 4 * st + (lane >> 3), t = lane & 7;
+                    bool      hit[4] = { false, false, false, false };
                     if (q < nq)
                     {
-                        const uint4  pq = S.pairQ[warp][q];
-                        const size_t chunk = (size_t)pq.x | ((size_t)pq.y << 32);
-                        const float2 d = __ldg(R.disk + chunk * 32 + lane);
-                        const int    cell = (__float2int_rd(d.y * 4.f) + 4) * 8 + (__float2int_rd(d.x * 4.f) + 4);  // = cell_of(y) * 8 + cell_of(x): scaling by 4 is exact
-                        hm[q] = __ballot_sync(0xffffffffu, (S.rowE[pq.z / NW] >> cell) & 1ull);
+                        const uint4              pq = S.pairQ[warp][q];
+                        const size_t             chunk = (size_t)pq.x | ((size_t)pq.y << 32);
+                        const float4*            src = reinterpret_cast<const float4*>(R.disk + chunk * 32 + 4 * t);
+                        const float4             s01 = __ldg(src), s23 = __ldg(src + 1);
+                        const unsigned long long E = S.rowE[pq.z / NW];
+                        // cell = cell_of(y) * 8 + cell_of(x): scaling by 4 is exact
+                        hit[0] = (E >> ((__float2int_rd(s01.y * 4.f) + 4) * 8 + (__float2int_rd(s01.x * 4.f) + 4))) & 1ull;
+                        hit[1] = (E >> ((__float2int_rd(s01.w * 4.f) + 4) * 8 + (__float2int_rd(s01.z * 4.f) + 4))) & 1ull;
+                        hit[2] = (E >> ((__float2int_rd(s23.y * 4.f) + 4) * 8 + (__float2int_rd(s23.x * 4.f) + 4))) & 1ull;
+                        hit[3] = (E >> ((__float2int_rd(s23.w * 4.f) + 4) * 8 + (__float2int_rd(s23.z * 4.f) + 4))) & 1ull;
                     }
-                    cum[q + 1] = cum[q] + __popc(hm[q]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        hm[4 * st + j] = __ballot_sync(0xffffffffu, hit[j]);
+                        cum[4 * st + j + 1] = cum[4 * st + j] + __popc(hm[4 * st + j]);
+                    }
                 }
                 for (int base = 0; base < cum[8]; base += 32)
                 {
                     const int hi = base + lane;
                     if (hi < cum[8])
                     {
-                        int      q = 0, c0 = 0;
+                        int      wq = 0, c0 = 0;
                         uint32_t m = hm[0];
 #pragma unroll
                         for (int jq = 1; jq < 8; ++jq)
-                            if (cum[jq] <= hi) q = jq, c0 = cum[jq], m = hm[jq];
-                        const int    tap = nth_set_bit(m, hi - c0);
+                            if (cum[jq] <= hi) wq = jq, c0 = cum[jq], m = hm[jq];
+                        const int    bit = nth_set_bit(m, hi - c0);
+                        const int    q = 4 * (wq >> 2) + (bit >> 3), tap = 4 * (bit & 7) + (wq & 3);
                         const uint4  pq = S.pairQ[warp][q];
                         const size_t chunk = (size_t)pq.x | ((size_t)pq.y << 32);
                         const float2 d = __ldg(R.disk + chunk * 32 + tap);
@@ -949,15 +966,63 @@ __global__ void __launch_bounds__(256) k_pixel_flags(size_t n, const int* isU, c
     if (idx >= n) return;
     hasBlocker[idx] = isU[idx] ? (int)flagU[posU[idx]] : isC1[idx];
 }
-// chunk index of every pixel, visibility 1 for the pixels without a blocker (shadow.cpp:96-99), list of the others
+// chunk index of every pixel, visibility 1 for the pixels without a blocker (shadow.cpp:96-99), list of the others.
+//
+// Deep-shadow shortcut (exact): a site whose 32 search taps all block (class "certain") has an average blocker depth of
+// at least zbLo = (1 - 4e-6) min(search box) (ordered fp32 sum of 32 values >= that minimum), hence a penumbra of at most
+// (z - zbLo) A / zbLo and a PCF filter radius of at most F = pcfFilter * penumbra (monotone in the blocker depth; 1e-5
+// of slack for the fp32 roundings).  If all texels within ceil(iw F) + 2 of the site's texel fail the depth test —
+// z > max(box) + bias, the box maximum assembled from k x k look-ups of the search-radius maximum map, k <= 4 — and
+// no tap can leave the map, every one of the 64 PCF taps fails, and the visibility is exactly 0 / 64.
+struct DeepShadow
+{
+    const int*   isC1;
+    const float4* sc4;
+    const float *smMin, *smMax;
+    ShadowMapD   sm;
+    int          r;  // radius of the smMin / smMax boxes
+    double       pcfFilter;
+    float        areaLight;
+};
 __global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long long base, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis,
-                                                     unsigned* blockerList, unsigned* nBlockers)
+                                                     unsigned* blockerList, unsigned* nBlockers, DeepShadow D)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     chunkOf[idx] = (unsigned)(base + idx + 2ull * (unsigned)kpre[idx]);
-    vis[idx] = 1.f;
-    if (hasB[idx]) blockerList[kpre[idx]] = (unsigned)idx;
+    float v = 1.f;
+    if (hasB[idx])
+    {
+        unsigned entry = (unsigned)idx;
+        if (D.isC1[idx])
+        {
+            const float4 s = D.sc4[idx];
+            // centre texel as k_classify computed it (a certain site has all its search taps, hence its centre, inside the map)
+            const int    cx = (int)((float)D.sm.iw * clampf(s.x, 0.f, 1.f)), cy = (int)((float)D.sm.ih * clampf(s.y, 0.f, 1.f));
+            const float  dmin = D.smMin[(size_t)cy * D.sm.w + cx];
+            if (dmin >= 0.002f && s.z == s.z)
+            {
+                const double zbLo = (double)dmin * (1.0 - 4e-6);
+                const double F = D.pcfFilter * (((double)s.z - zbLo) * (double)D.areaLight / zbLo) * (1.0 + 1e-5);
+                const bool   inside = F >= 0.0 && (double)s.x - F >= 1e-6 && (double)s.x + F <= 1.0 - 1e-6 && (double)s.y - F >= 1e-6 && (double)s.y + F <= 1.0 - 1e-6;
+                const double rp = ceil((double)max(D.sm.iw, D.sm.ih) * F) + 2.0;
+                if (inside && rp <= 4.0 * D.r)
+                {
+                    const int k = max(1, ((int)rp + D.r - 1) / D.r);
+                    float     mx = -__int_as_float(0x7f800000);
+                    for (int j = 0; j < k; ++j)
+                        for (int i = 0; i < k; ++i)
+                        {
+                            int x = min(max(cx - (k - 1) * D.r + 2 * D.r * i, 0), D.sm.w - 1), y = min(max(cy - (k - 1) * D.r + 2 * D.r * j, 0), D.sm.h - 1);
+                            mx = fmaxf(mx, __ldg(D.smMax + (size_t)y * D.sm.w + x));
+                        }
+                    if (s.z > mx + s.w) v = 0.f, entry = 0xffffffffu;
+                }
+            }
+        }
+        blockerList[kpre[idx]] = entry;
+    }
+    vis[idx] = v;
     if (idx == n - 1) *nBlockers = (unsigned)(kpre[idx] + hasB[idx]);
 }
 
@@ -984,6 +1049,7 @@ __global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blocker
     for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nWarps)
     {
         unsigned idx = blockerList[i];
+        if (idx == 0xffffffffu) continue;  // deep in shadow: visibility 0 already written (k_chunk_index)
         float4   s = sc4[idx];
         size_t   first = (size_t)chunkOf[idx] * 32;
         float2   d0 = __ldg(disk + first + lane), d1 = __ldg(disk + first + 32 + lane), d2 = __ldg(disk + first + 64 + lane);
@@ -1260,7 +1326,8 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
                     attr = true;
                 }
                 k_minmax_h<true><<<dim3((L.sm.w + kMMW - 1) / kMMW, L.sm.h), 256, 0, st>>>(L.sm.d, nullptr, L.sm.w, L.sm.h, lo, hi, tmin, tmax);
-                k_minmax_v<<<dim3((L.sm.w + 31) / 32, (L.sm.h + kMMR - 1) / kMMR), 512, 2 * 256 * 32 * 8, st>>>(tmin, tmax, L.sm.w, L.sm.h, lo, hi, omin, omax);
+                k_minmax_v<<<dim3((L.sm.w + 31) / 32, (L.sm.h + kMMR - 1) / kMMR), 512, (size_t)2 * (kMMR + w - 1) * 32 * 8, st>>>(tmin, tmax, L.sm.w, L.sm.h, lo, hi, omin,
+                                                                                                                                  omax);
             }
             else
             {
@@ -1385,8 +1452,11 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     if (int rc = scan_ints(c, (const int*)s->hasB.p, (int*)s->kpre.p, n)) return rc;
     {
         LaunchScope ls(c, "pcss_chunk_index", n * 20);
+        DeepShadow D;
+        D.isC1 = (const int*)s->isC1.p, D.sc4 = sc4In, D.smMin = (const float*)s->smMin.p, D.smMax = (const float*)s->smMax.p, D.sm = L.sm, D.r = r;
+        D.pcfFilter = L.pcfFilter, D.areaLight = L.areaLight;
         k_chunk_index<<<nb, 256, 0, st>>>(n, chunkBase, (const int*)s->kpre.p, (const int*)s->hasB.p, chunkOfB, visB, (unsigned*)s->blockerList.p,
-                                          (unsigned*)s->mState.p + CH_NBLOCKERS);
+                                          (unsigned*)s->mState.p + CH_NBLOCKERS, D);
     }
     {
         LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
