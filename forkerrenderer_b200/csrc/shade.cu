@@ -345,6 +345,70 @@ __global__ void __launch_bounds__(256) k_blur_v(float* a, int W, int H, int rowB
     }
 }
 
+// ---- in-place 3x3 box (buffer.cpp:35-57 / 140-162) --------------------------------------------------------------------
+// Pixel (w, h) reads row h - 1 and (w - 1, h) already blurred and everything else still original (raster order, in
+// place, clamped taps that read "whatever is there"), so the pixels of a wavefront t = w + 2 h are independent.  One CTA
+// walks up to 1024 rows in lockstep: thread = row, row i lags row i - 1 by two columns, one __syncthreads per step; the
+// blurred value of the row above travels through a shared-memory slot, the originals of the own row and of the row
+// below are fetched eight steps at a time.  Not on the frame path (Render::Render never calls it): latency-bound by
+// design, (W + 2 min(H, 1024)) steps per pass of 1024 rows.
+__global__ void __launch_bounds__(1024) k_simple_blur(float* a, int W, int H, int rowBase, int nRows)
+{
+    __shared__ float exch[2][1024];
+    const int   i = threadIdx.x, h = rowBase + i;
+    const bool  live = i < nRows;
+    const bool  topRow = h == 0, bottomRow = h == H - 1, fromGlobal = i == 0 && h > 0;
+    const float s = 1 / 9.f;
+    float       up0 = 0.f, up1 = 0.f, up2 = 0.f;  // blurred row h - 1 at w - 1, w, w + 1
+    float       oL = 0.f, oM = 0.f, oR = 0.f;      // own row: blurred (w - 1), original w, original w + 1
+    float       dn0 = 0.f, dn1 = 0.f, dn2 = 0.f;  // original row h + 1 at w - 1, w, w + 1
+    const int   tEnd = W - 1 + 2 * (nRows - 1);   // last step (the first is -1: every row has a set-up step at w = -1)
+    for (int T0 = -1; T0 <= tEnd; T0 += 8)
+    {
+        float bo[8], bd[8], bu[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            const int w = T0 + k - 2 * i;
+            bo[k] = bd[k] = bu[k] = 0.f;
+            if (live && w >= -1 && w <= W - 1)
+            {
+                const int c = min(w + 1, W - 1);
+                bo[k] = a[(size_t)h * W + c];
+                if (!bottomRow) bd[k] = a[(size_t)(h + 1) * W + c];
+                if (fromGlobal) bu[k] = a[(size_t)(h - 1) * W + c];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            const int t = T0 + k, w = t - 2 * i;
+            if (live && w >= -1 && w <= W - 1)
+            {
+                float newU = up2;
+                if (w + 1 <= W - 1 && !topRow) newU = fromGlobal ? bu[k] : exch[(t - 1) & 1][i - 1];
+                up0 = up1, up1 = up2, up2 = newU;
+                oM = oR, oR = bo[k];
+                dn0 = dn1, dn1 = dn2, dn2 = bd[k];
+                if (w >= 0)
+                {
+                    const float xl = w == 0 ? oM : oL, xm = oM, xr = oR;  // the own row as it stands: (w - 1) blurred, the rest original
+                    const float al = topRow ? xl : (w == 0 ? up1 : up0), am = topRow ? xm : up1, ar = topRow ? xr : up2;
+                    const float bl = bottomRow ? xl : (w == 0 ? dn1 : dn0), bm = bottomRow ? xm : dn1, br = bottomRow ? xr : dn2;
+                    float       r = 0.f;
+                    r += al * s, r += xl * s, r += bl * s;  // xOffset = -1: yOffset = -1, 0, +1
+                    r += am * s, r += xm * s, r += bm * s;
+                    r += ar * s, r += xr * s, r += br * s;
+                    a[(size_t)h * W + w] = r;
+                    exch[t & 1][i] = r;
+                    oL = r;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ---- SSAO, one warp per pixel: lane = hemisphere sample (render.cpp:229-285) -----------------------------------------
 // The kernel is bound by instruction issue (profiles/), so the arithmetic that cannot change the result is trimmed:
 //  * VIEWPORT_AFFINE: ForkerGL::SetViewportMatrix (forkergl.cpp:89-102) only fills [0][0], [0][3], [1][1], [1][3], [2][2],
@@ -484,9 +548,20 @@ int fgl_run_ssaa(fgl_ctx* c, const uint8_t* rgb8, int W, int H, int k, uint8_t* 
 
 int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind, int hRow0, int hRow1, int vRow0, int vRow1)
 {
-    if (kind != FGL_BLUR_TWO_PASS_GAUSSIAN)
-        return fgl_fail(c, FGL_ERR_UNSUPPORTED, "fgl_blur: the in-place 3x3 box (buffer.cpp:35-57) is not on the frame path and has no device kernel yet");
     size_t n = (size_t)W * H;
+    if (kind == FGL_BLUR_SIMPLE_3X3)
+    {
+        if (hRow0 != 0 || hRow1 != H || vRow0 != 0 || vRow1 != H)
+            return fgl_fail(c, FGL_ERR_UNSUPPORTED, "fgl_blur: the in-place 3x3 box is a whole-plane recurrence (no row bands)");
+        for (int ch = 0; ch < channels; ++ch)
+            for (int row = 0; row < H; row += 1024)
+            {
+                LaunchScope ls(c, "simple_blur", (uint64_t)W * std::min(1024, H - row) * 8);
+                k_simple_blur<<<1, 1024, 0, c->stream>>>(plane + ch * n, W, H, row, std::min(1024, H - row));
+            }
+        return check_launch(c, "simple blur");
+    }
+    if (kind != FGL_BLUR_TWO_PASS_GAUSSIAN) return fgl_fail(c, FGL_ERR_INVALID, "fgl_blur: unknown blur kind");
     for (int ch = 0; ch < channels; ++ch)
     {
         {

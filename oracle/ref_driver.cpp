@@ -138,8 +138,60 @@ void DumpIds(const std::string& path, const Scene& scene, bool lightSpace, int w
 }
 }  // namespace
 
+// --buffer-test OUTDIR: the reference's own Buffer1f / Buffer3f post-processing (buffer.cpp:35-98, 140-203) on
+// deterministic inputs (an LCG, restated in tests/parity.py), raw results dumped for tests/golden/make_golden.py.
+static float Lcg01(uint32_t& s)
+{
+    s = s * 1664525u + 1013904223u;
+    return (float)((s >> 8) & 0xffffffu) / 16777216.f;
+}
+static int BufferTest(const std::string& out)
+{
+    const int shapes[][2] = { { 5, 4 }, { 33, 7 }, { 1, 9 }, { 9, 1 }, { 64, 48 } };
+    for (auto& sh : shapes)
+    {
+        const int W = sh[0], H = sh[1];
+        for (int kind = 0; kind < 2; ++kind)
+        {
+            uint32_t seed = 12345u + (uint32_t)(W * 131 + H);
+            Buffer1f b1(W, H, Buffer::Zero);
+            Buffer3f b3(W, H, Buffer::Zero);
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) b1.SetValue(x, y, Lcg01(seed));
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x)
+                {
+                    float r = Lcg01(seed), g = Lcg01(seed), bb = Lcg01(seed);
+                    b3.SetValue(x, y, Vector3f(r, g, bb));
+                }
+            if (kind == 0) b1.SimpleBlurDenoised(), b3.SimpleBlurDenoised();
+            else b1.TwoPassGaussianBlurDenoised(), b3.TwoPassGaussianBlurDenoised();
+            char name[256];
+            snprintf(name, sizeof name, "%s/buffer_%s_%dx%d.raw", out.c_str(), kind == 0 ? "simple" : "gauss", W, H);
+            FILE* f = fopen(name, "wb");
+            if (!f) return 3;
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x)
+                {
+                    float v = b1.GetValue(x, y);
+                    fwrite(&v, 4, 1, f);
+                }
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x)
+                {
+                    Vector3f v = b3.GetValue(x, y);
+                    float    q[3] = { v.x, v.y, v.z };
+                    fwrite(q, 4, 3, f);
+                }
+            fclose(f);
+        }
+    }
+    return 0;
+}
+
 int main(int argc, const char* argv[])
 {
+    if (argc == 3 && std::string(argv[1]) == "--buffer-test") return BufferTest(argv[2]);
     std::string assets = ".", sceneFile, out = ".", shadow = "pcss";
     int         wrap = 0, filter = 0, frames = 1;
     bool        ids = false, tga = false, quiet = false;

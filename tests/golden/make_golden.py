@@ -29,7 +29,11 @@ def fingerprint(a):
 def main():
     out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_hashes.json")
     golden = json.load(open(out_path)) if os.path.exists(out_path) else {}
-    cfgs = sys.argv[1:] or list(P.CONFIGS)
+    cfgs = sys.argv[1:] or (list(P.CONFIGS) + ["buffer_ops"])
+    if "buffer_ops" in cfgs:  # Buffer1f / Buffer3f SimpleBlurDenoised and TwoPassGaussianBlurDenoised (buffer.cpp:35-98, 140-203)
+        cfgs.remove("buffer_ops")
+        golden["buffer_ops"] = {k: {"buffer1f": fingerprint(v[0]), "buffer3f": fingerprint(v[1])} for k, v in sorted(P.run_reference_buffer_ops().items())}
+        print("buffer_ops ok", flush=True)
     for cfg in cfgs:
         ref = P.run_reference(cfg)
         meta = ref.pop("meta")

@@ -33,6 +33,46 @@ CONFIGS = {
 }
 
 
+BUFFER_SHAPES = [(5, 4), (33, 7), (1, 9), (9, 1), (64, 48)]
+BUFFER_KINDS = {"simple": B.BLUR_SIMPLE_3X3, "gauss": B.BLUR_TWO_PASS_GAUSSIAN}
+
+
+def buffer_test_inputs(W, H):
+    """The deterministic Buffer1f / Buffer3f contents of `ref_driver --buffer-test` (an LCG): (H, W) and (H, W, 3) float32."""
+    s = np.uint32(12345 + W * 131 + H)
+    out = np.empty(W * H * 4, dtype=np.float32)
+    a, c = np.uint32(1664525), np.uint32(1013904223)
+    with np.errstate(over="ignore"):
+        for i in range(out.size):
+            s = np.uint32(s * a + c)
+            out[i] = np.float32((int(s) >> 8) & 0xffffff) / np.float32(16777216.0)
+    return out[: W * H].reshape(H, W).copy(), out[W * H:].reshape(H, W, 3).copy()
+
+
+def run_reference_buffer_ops(out_dir=None):
+    """{"simple_WxH" / "gauss_WxH": (Buffer1f result, Buffer3f result)} from the UNMODIFIED reference's Buffer classes."""
+    out_dir = out_dir or os.path.join(tempfile.gettempdir(), "fgl_ref_buffer_ops")
+    os.makedirs(out_dir, exist_ok=True)
+    subprocess.run([REF_DRIVER, "--buffer-test", out_dir], check=True)
+    res = {}
+    for kind in BUFFER_KINDS:
+        for W, H in BUFFER_SHAPES:
+            raw = np.fromfile(os.path.join(out_dir, "buffer_%s_%dx%d.raw" % (kind, W, H)), dtype=np.float32)
+            res["%s_%dx%d" % (kind, W, H)] = (raw[: W * H].reshape(H, W), raw[W * H:].reshape(H, W, 3))
+    return res
+
+
+def blur_through_abi(fgl, kind, a1, a3):
+    """Buffer1f / Buffer3f post-processing through the C ABI: the AO plane and the albedo plane stand in for the buffers."""
+    H, W = a1.shape
+    fgl.init_geometry_buffers(W, H)
+    fgl.write_plane("ao", a1)
+    fgl.write_plane("albedo", a3)
+    fgl.blur(B.PLANE_AO, kind)
+    fgl.blur(B.PLANE_ALBEDO, kind)
+    return fgl.read_plane("ao"), fgl.read_plane("albedo")
+
+
 def have_ref():
     return os.path.exists(REF_DRIVER) and os.path.isdir(os.path.join(ASSETS, "obj"))
 

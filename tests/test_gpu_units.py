@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import parity as P
+from conftest import sha as P_sha
 import test_oracle_units as U
 from forkerrenderer_b200 import binding as B
 
@@ -58,6 +59,27 @@ def test_three_channel_blur(gpu_fgl, oracle_fgl):
         f.write_plane("albedo", a)
         f.blur(B.PLANE_ALBEDO, B.BLUR_TWO_PASS_GAUSSIAN)
     assert np.array_equal(gpu_fgl.read_plane("albedo"), oracle_fgl.read_plane("albedo"))
+
+
+@pytest.mark.parametrize("kind", sorted(P.BUFFER_KINDS))
+def test_buffer_post_processing_matches_reference(kind, gpu_fgl, golden):
+    """Both Buffer blurs on the device against the reference's own Buffer classes (tests/golden, `buffer_ops`)."""
+    for W, H in P.BUFFER_SHAPES:
+        a1, a3 = P.buffer_test_inputs(W, H)
+        g1, g3 = P.blur_through_abi(gpu_fgl, P.BUFFER_KINDS[kind], a1, a3)
+        want = golden["buffer_ops"]["%s_%dx%d" % (kind, W, H)]
+        assert P_sha(g1) == want["buffer1f"]["sha256"], (kind, W, H, "Buffer1f")
+        assert P_sha(g3) == want["buffer3f"]["sha256"], (kind, W, H, "Buffer3f")
+
+
+def test_simple_blur_wavefront_across_passes(gpu_fgl, oracle_fgl):
+    """The in-place 3x3 box is a wavefront over the whole plane; more than 1024 rows take several kernel passes."""
+    rng = np.random.RandomState(23)
+    for (W, H) in ((300, 1100), (7, 2050), (1500, 3)):
+        a1, a3 = rng.rand(H, W).astype(np.float32), rng.rand(H, W, 3).astype(np.float32)
+        g = P.blur_through_abi(gpu_fgl, B.BLUR_SIMPLE_3X3, a1, a3)
+        o = P.blur_through_abi(oracle_fgl, B.BLUR_SIMPLE_3X3, a1, a3)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]), (W, H)
 
 
 def test_ssaa_box(gpu_fgl, oracle_fgl):

@@ -49,3 +49,15 @@ def test_golden_was_generated_by_the_reference_when_it_is_here(golden):
     ref = P.run_reference("c1_hard")
     for name in ("depth", "frame_u8", "ids_camera", "normal"):
         assert sha(ref[name]) == golden["c1_hard"]["planes"][name]["sha256"], name
+
+
+@pytest.mark.parametrize("kind", sorted(P.BUFFER_KINDS))
+def test_oracle_buffer_post_processing_matches_reference(kind, oracle_fgl, golden):
+    """Buffer1f/3f::SimpleBlurDenoised and ::TwoPassGaussianBlurDenoised (buffer.cpp:35-98, 140-203): the in-place raster-order
+    semantics, against fingerprints of the reference's own Buffer classes on the same LCG inputs."""
+    for W, H in P.BUFFER_SHAPES:
+        a1, a3 = P.buffer_test_inputs(W, H)
+        g1, g3 = P.blur_through_abi(oracle_fgl, P.BUFFER_KINDS[kind], a1, a3)
+        want = golden["buffer_ops"]["%s_%dx%d" % (kind, W, H)]
+        assert sha(g1) == want["buffer1f"]["sha256"], (kind, W, H, "Buffer1f")
+        assert sha(g3) == want["buffer3f"]["sha256"], (kind, W, H, "Buffer3f")

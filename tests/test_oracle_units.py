@@ -106,3 +106,17 @@ def test_ssaa_integer_box(oracle_fgl):
     want = (q.reshape(3, 2, 4, 2, 3).sum(axis=(1, 3)) / 4.0).astype(np.int64).astype(np.uint8)
     assert np.array_equal(f.read_plane("ssaa_u8"), want)
     assert np.array_equal(f.read_plane("frame_u8"), q.astype(np.uint8))
+
+
+def test_host_alloc_backs_plane_reads(oracle_fgl):
+    """fgl_host_alloc / fgl_host_free (page-locked memory in the product, malloc in the oracle): read_plane(pinned=True)
+    returns the same data as a pageable read and reuses its buffer."""
+    rng = np.random.RandomState(3)
+    a = rng.rand(6, 9).astype(np.float32)
+    oracle_fgl.init_geometry_buffers(9, 6)
+    oracle_fgl.write_plane("ao", a)
+    p1 = oracle_fgl.read_plane("ao", pinned=True)
+    assert np.array_equal(p1, a) and np.array_equal(oracle_fgl.read_plane("ao"), a)
+    oracle_fgl.write_plane("ao", a * 2)
+    p2 = oracle_fgl.read_plane("ao", pinned=True)
+    assert p2.ctypes.data == p1.ctypes.data and np.array_equal(p2, a * 2)
