@@ -234,6 +234,9 @@ class Fgl:
         self.call("fgl_draw_screen_space_pixels", (C.c_float * 3)(*eye), (C.c_float * 3)(*light_pos),
                   (C.c_float * 3)(*light_color))
 
+    def prepare_screen_space_pixels(self, eye, light_pos, light_color):
+        self.call("fgl_prepare_screen_space_pixels", (C.c_float * 3)(*eye), (C.c_float * 3)(*light_pos), (C.c_float * 3)(*light_color))
+
     # ---- buffers
     def plane_info(self, plane):
         w, h, ch, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()

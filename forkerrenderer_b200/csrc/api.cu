@@ -590,9 +590,9 @@ int fgl_draw_mesh(fgl_ctx* c, int meshId, int kind, const FglUniforms* un)
     return FGL_OK;
 }
 
-int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3])
+// LightPass of the lighting loop (forkergl.cpp:326-380) for the current state; shared by the two entry points below
+static int build_light_pass(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3], LightPass& L, bool& fullBand)
 {
-    ENTER(c);
     if (!eye || !lpos || !lcol) return fgl_fail(c, FGL_ERR_INVALID, "NULL argument");
     if (int rc = flush(c)) return rc;
     PlaneH& frame = c->planes[FGL_PLANE_FRAME];
@@ -604,7 +604,6 @@ int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpo
         if (!q.buf.p || q.w != frame.w || q.h != frame.h) return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels: G-buffers missing or of another size");
         if (int rc = materialize(c, pl)) return rc;
     }
-    LightPass L;
     memset(&L, 0, sizeof L);
     L.W = frame.w, L.H = frame.h;
     band_of(c, L.H, L.row0, L.row1);
@@ -619,18 +618,41 @@ int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpo
         L.sm = shadow_map_dev(c);
     }
     memcpy(L.eye, eye, 12), memcpy(L.lightPos, lpos, 12), memcpy(L.lightColor, lcol, 12);
-    bool fullBand = L.row0 == 0 && L.row1 == L.H;
+    fullBand = L.row0 == 0 && L.row1 == L.H;
+    L.planes = planes_dev(c);
+    return FGL_OK;
+}
+
+// Optional first half of fgl_draw_screen_space_pixels: everything of a PCSS frame that does not depend on the bands above
+// this one (shadow coordinates, min/max maps, classification, cell masks, the pilot).  A sort-first driver calls it
+// before it waits for the previous band's blocker count; single-GPU callers never need it.
+int fgl_prepare_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3])
+{
+    ENTER(c);
+    LightPass L;
+    bool      fullBand = false;
+    if (int rc = build_light_pass(c, eye, lpos, lcol, L, fullBand)) return rc;
+    if (c->shadowOn && c->params.shadow_mode == FGL_SHADOW_PCSS) return fgl_stream_prepare_lighting(c, L, FGL_VIS_PREPARE);
+    return FGL_OK;
+}
+
+int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3])
+{
+    ENTER(c);
+    LightPass L;
+    bool      fullBand = false;
+    if (int rc = build_light_pass(c, eye, lpos, lcol, L, fullBand)) return rc;
+    PlaneH& frame = c->planes[FGL_PLANE_FRAME];
     if (L.writeF32)
     {
         if (fullBand) frame.fillPending = false;
         else if (int rc = materialize(c, FGL_PLANE_FRAME)) return rc;
     }
-    L.planes = planes_dev(c);
     size_t n = (size_t)L.W * L.H;
     if (int rc = fgl_reserve(c, c->frameRgb8, n * 3 + 16)) return rc;
     L.rgb8 = (uint8_t*)c->frameRgb8.p;
     if (c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD)
-        if (int rc = fgl_stream_prepare_lighting(c, L)) return rc;
+        if (int rc = fgl_stream_prepare_lighting(c, L, FGL_VIS_RESOLVE)) return rc;  // continues a prepared chain, else does it all
     if (int rc = fgl_run_lighting(c, L)) return rc;
     c->frameRgb8Valid = fullBand;  // with a partial band only the band rows are current; readers take rows of the band
     c->bandRgb8Valid = true;

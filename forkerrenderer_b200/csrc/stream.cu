@@ -1114,6 +1114,10 @@ struct SampleStream
     DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
     DevBuf sig, vis, blockerList, pilot, Ppre, winLo, chainStats, rowBits;
     unsigned long long sigChunks = 0;
+    // FGL_VIS_PREPARE -> FGL_VIS_RESOLVE hand-over
+    bool               prepValid = false;
+    size_t             prepTotal = 0, prepLo = 0, prepHi = 0;
+    int                prepNU = 0, prepNC1 = 0;
     unsigned long long chainTotal = 0;  // blockers found up to and including this context's band
     bool               chainCountValid = false;
 };
@@ -1140,6 +1144,7 @@ void fgl_stream_destroy(fgl_ctx* c)
 void fgl_stream_begin_frame(fgl_ctx* c)
 {
     SampleStream* s = S_of(c);
+    s->prepValid = false;
     s->ssaoThisFrame = false;
     s->ssaoSamples = 0;
 }
@@ -1251,7 +1256,8 @@ static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
 
 // Visibility of n stream consumers ("sites") in consumption order, given their shadow coordinate + bias.
 // [siteLo, siteHi) = the sites whose visibility is needed (PCF); PCSS resolves the whole chain.
-int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const float4* sc4All, size_t siteLo, size_t siteHi, unsigned long long blockersBefore)
+int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const float4* sc4All, size_t siteLo, size_t siteHi, unsigned long long blockersBefore,
+                               int phase)
 {
     size_t n = nTotal;  // table sizes follow the whole site set; the kernels below work on [siteLo, siteHi)
 
@@ -1285,6 +1291,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     P.sm = L.sm;
     if (!pcss)
     {
+        if (phase == FGL_VIS_PREPARE) return FGL_OK;  // PCF offsets are closed-form: nothing depends on earlier bands
         size_t      nSites = siteHi - siteLo;
         LaunchScope ls(c, "pcf_visibility", nSites * (16 + 512 + 4));
         if (nSites) k_pcf_visibility<<<(unsigned)((nSites * 32 + 255) / 256), 256, 0, st>>>(L.sm, siteLo, siteHi, sc4All, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
@@ -1312,6 +1319,19 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     if (!((double)fsF >= L.pcssFilter)) fsF = nextafterf(fsF, 1e30f);  // |(float)(d * fs)| <= fsF for |d| < 1
     int r = (int)ceil((double)L.sm.iw * (double)fsF) + 1;
     int bw = (int)ceil(0.25 * (double)L.sm.iw * (double)fsF) + 2;
+    unsigned nb = (unsigned)((n + 255) / 256);
+    int      nU = 0, nC1 = 0;  // uncertain sites; sites whose every tap blocks
+    // Everything up to the pilot's prefix sums is independent of the blockers found in earlier bands: a sort-first
+    // driver runs it (FGL_VIS_PREPARE) while it waits for the previous band's count, then resolves (FGL_VIS_RESOLVE).
+    const bool prepared = phase == FGL_VIS_RESOLVE && s->prepValid && s->prepTotal == nTotal && s->prepLo == siteLo && s->prepHi == siteHi;
+    if (prepared) nU = s->prepNU, nC1 = s->prepNC1;
+    s->prepValid = false;
+    ChainRows R;
+    memset(&R, 0, sizeof R);
+    R.sm = L.sm, R.disk = L.disk, R.fs = L.pcssFilter, R.sig = (const unsigned long long*)s->sig.p;
+    R.base = phase == FGL_VIS_PREPARE ? (unsigned long long)siteLo : chunkBase;  // the pilot only predicts: any nearby offset will do
+    if (!prepared)
+    {
     {
         LaunchScope ls(c, "pcss_minmax", smN * 48);
         auto box = [&](int lo, int hi, float* omin, float* omax) -> int {
@@ -1342,7 +1362,6 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         c->launches += 3;
     }
     P.smMin = (const float*)s->smMin.p, P.smMax = (const float*)s->smMax.p, P.r = r, P.fsF = fsF;
-    unsigned nb = (unsigned)((n + 255) / 256);
     {
         LaunchScope ls(c, "pcss_classify", n * (16 + 8));
         k_classify<<<nb, 256, 0, st>>>(P, n, sc4In, (int*)s->isU.p, (int*)s->isC1.p);
@@ -1351,11 +1370,9 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     FGL_CUDA(c, cudaMemsetAsync((int*)s->isC1.p + n, 0, 4, st));
     if (int rc = scan_ints(c, (const int*)s->isU.p, (int*)s->posU.p, n + 1)) return rc;
     if (int rc = scan_ints(c, (const int*)s->isC1.p, (int*)s->c1pre.p, n + 1)) return rc;
-    int nU = 0, nC1 = 0;  // uncertain sites; sites whose every tap blocks
     FGL_CUDA(c, cudaMemcpyAsync(&nU, (int*)s->posU.p + n, 4, cudaMemcpyDeviceToHost, st));
     FGL_CUDA(c, cudaMemcpyAsync(&nC1, (int*)s->c1pre.p + n, 4, cudaMemcpyDeviceToHost, st));
     FGL_CUDA(c, cudaStreamSynchronize(st));
-    unsigned long long uncertainBlockers = 0;
     if (int rc = fgl_reserve(c, s->Upix, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Uc1, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Usc, (size_t)(nU + 1) * 16)) return rc;
@@ -1377,11 +1394,8 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
             k_pixel_masks<<<(unsigned)(((size_t)nU * 32 + 255) / 256), 256, 0, st>>>(M, nU, (const float4*)s->Usc.p, (unsigned long long*)s->UF.p,
                                                                                     (unsigned long long*)s->UE.p);
         }
-        FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 64, st));
-        ChainRows R;
         R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
-        R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p, R.sig = (const unsigned long long*)s->sig.p;
-        R.sm = L.sm, R.disk = L.disk, R.fs = L.pcssFilter, R.base = chunkBase;
+        R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p;
         static const bool wantStats = getenv("FGL_CHAIN_STATS") != nullptr;
         R.stats = nullptr;
         if (wantStats)
@@ -1398,6 +1412,22 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         }
         FGL_CUDA(c, cudaMemsetAsync((int*)s->pilot.p + nU, 0, 4, st));
         if (int rc = scan_ints(c, (const int*)s->pilot.p, (int*)s->Ppre.p, (size_t)nU + 1)) return rc;
+    }
+    }  // !prepared
+    if (phase == FGL_VIS_PREPARE)
+    {
+        s->prepValid = true, s->prepTotal = nTotal, s->prepLo = siteLo, s->prepHi = siteHi, s->prepNU = nU, s->prepNC1 = nC1;
+        return FGL_OK;
+    }
+    unsigned long long uncertainBlockers = 0;
+    c->lastUncertain = nU;
+    if (nU > 0)
+    {
+        R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
+        R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p;
+        R.base = chunkBase;
+        R.stats = s->chainStats.p && getenv("FGL_CHAIN_STATS") ? (unsigned long long*)s->chainStats.p : nullptr;
+        FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 64, st));
         {
             // persistent cooperative kernel: one CTA per SM, all co-resident (the launch fails otherwise)
             static int nSM = 0, segsEnv = getenv("FGL_CHAIN_SEGS") ? atoi(getenv("FGL_CHAIN_SEGS")) : 0;
@@ -1473,7 +1503,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
 }
 
 // Deferred lighting: the sites are the pixels in scan order (forkergl.cpp:336-378 visits every pixel, background included).
-int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
+int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase)
 {
     SampleStream* s = S_of(c);
     size_t        n = (size_t)L.W * L.H;
@@ -1487,12 +1517,13 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L)
     bool   pcss = L.shadowMode == FGL_SHADOW_PCSS;
     size_t lo = (size_t)L.row0 * L.W, hi = (size_t)L.row1 * L.W;
     (void)pcss;
+    if (!(phase == FGL_VIS_RESOLVE && s->prepValid))
     {
         LaunchScope ls(c, "shadow_coords", (hi - lo) * (36 + 16));
         k_shadow_coords<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(P, lo, hi, (float4*)s->sc4.p);
     }
     // sort-first bands: the chain of this band starts from the number of blockers found in the bands before it
-    return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, lo, hi, c->chainBlockersBefore);
+    return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, lo, hi, c->chainBlockersBefore, phase);
 }
 
 // Blockers found up to and including this context's band (= input of the next band's chain).  Does not touch the stream.

@@ -10,7 +10,10 @@ int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S);
 // Deferred lighting continues where SSAO stopped: PCF takes 64 accepted unit-disk samples per pixel, PCSS 32 plus
 // 64 more iff the pixel's blocker search found a blocker (shadow.cpp:92-106) — a frame-long dependency chain that
 // is resolved here into a per-pixel chunk index.
-int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L);
+// phase: the part of the PCSS resolution that does not depend on earlier bands (PREPARE), the rest (RESOLVE), or both.
+enum { FGL_VIS_ALL = 0, FGL_VIS_PREPARE = 1, FGL_VIS_RESOLVE = 2 };
+int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase = FGL_VIS_ALL);
 // Generic form: n consumers in consumption order with their shadow coordinate + bias (device array); leaves L.vis set.
-int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4, size_t siteLo, size_t siteHi, unsigned long long blockersBefore);
+int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4, size_t siteLo, size_t siteHi, unsigned long long blockersBefore,
+                               int phase = FGL_VIS_ALL);
 int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out);

@@ -214,6 +214,17 @@ void ForkerGL::DrawScreenSpacePixels(const Scene& scene)
     Check(fgl_draw_screen_space_pixels(Context(), e, p, c), "DrawScreenSpacePixels");
 }
 
+// sort-first drivers: the band-independent first half of DrawScreenSpacePixels (include/forkergl_b200.h)
+void ForkerGL::PrepareScreenSpacePixels(const Scene& scene)
+{
+    Point3f eye = scene.GetCamera().GetPosition();
+    Point3f lp = scene.GetPointLight().position;
+    Color3  lc = scene.GetPointLight().color;
+    float   e[3] = { eye.x, eye.y, eye.z }, p[3] = { lp.x, lp.y, lp.z }, c[3] = { lc.x, lc.y, lc.z };
+    InvalidateHostMirrors();
+    Check(fgl_prepare_screen_space_pixels(Context(), e, p, c), "PrepareScreenSpacePixels");
+}
+
 void ForkerGL::FetchAntiAliasedImage()
 {
     int w = 0, h = 0, ch = 0, bpc = 0;

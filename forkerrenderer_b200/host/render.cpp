@@ -57,6 +57,7 @@ void RenderGeometryStage(const Scene& scene)
         ForkerGL::SetPassType(ForkerGL::LightingPass);
         ForkerGL::ClearColor(Color3(0.12f, 0.12f, 0.12f));  // overwritten by the lighting loop, as in the reference
         if (scene.IsSSAOOn()) DoSSAO(scene);
+        ForkerGL::PrepareScreenSpacePixels(scene);  // nothing but a head start for the lighting loop (multi-GPU hand-off)
     }
 }
 

@@ -183,6 +183,8 @@ class SyntheticScene:
             if ssao:
                 f.ssao()
                 f.blur(B.PLANE_AO, B.BLUR_TWO_PASS_GAUSSIAN)
+            if band:  # sort-first: everything of the lighting pass that does not need the previous band's chain state
+                f.prepare_screen_space_pixels(self.eye, self.light_pos, self.light_color)
 
     def render_finish(self):
         f = self.f

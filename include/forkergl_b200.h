@@ -192,6 +192,11 @@ int fgl_draw_mesh(fgl_ctx* ctx, int mesh_id, int shader_kind, const FglUniforms*
 /* ForkerGL::DrawScreenSpacePixels (src/forkergl.cpp:326-380), the deferred lighting loop. */
 int fgl_draw_screen_space_pixels(fgl_ctx* ctx, const float eye_position[3], const float light_position[3],
                                  const float light_color[3]);
+/* Optional: the part of the lighting pass that does not depend on the row bands above this context's band (PCSS
+ * frames: shadow coordinates, classification, cell masks, pilot).  A sort-first multi-GPU driver calls it before it
+ * waits for the previous band's fgl_get_chain_blockers; fgl_draw_screen_space_pixels then only resolves the chain. */
+int fgl_prepare_screen_space_pixels(fgl_ctx* ctx, const float eye_position[3], const float light_position[3],
+                                    const float light_color[3]);
 
 /* Render::DoSSAO without its trailing blur (src/render.cpp:214-286) */
 int fgl_ssao(fgl_ctx* ctx);

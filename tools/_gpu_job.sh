@@ -1,5 +1,8 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r14_pytest.log
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r14_bench_c3.json 2> gpurun_out/r14_bench_c3.err
-timeout 600 python bench.py --workload c5 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r14_bench_c5.json 2> gpurun_out/r14_bench_c5.err
-tail -n 8 gpurun_out/r14_pytest.log
+N=$1
+export TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING=false
+run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 bench.py --gpus $N --steps $2 --warmup 3 --workload $3 --no-cpu-baseline > gpurun_out/r15_bench_$3_n$N.json 2> gpurun_out/r15_bench_$3_n$N.err; echo "rc=$?" >> gpurun_out/r15_bench_$3_n$N.err; }
+run 29511 10 c3
+run 29513 5 c5
+run 29515 20 c1
+tail -n 2 gpurun_out/r15_bench_c3_n$N.err gpurun_out/r15_bench_c5_n$N.err
