@@ -218,6 +218,10 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     fgl.set_stream(stream.cuda_stream)
     comm = M.TorchComm(dist, torch.device("cuda", local)) if world > 1 else None
+    # PCSS frames: the chain state goes from band to band through peer memory (device-side wait / peer store); --handoff host
+    # keeps the NCCL send / recv of one integer per band
+    peer = bool(world > 1 and r.pcss and args.handoff == "peer" and M.setup_peer_handoff(fgl, dist, rank, world, H))
+    _dbg("chain hand-off: %s" % ("peer memory" if peer else "host"))
     r0, r1, per = M.band_rows(H, world, rank)
     band = torch.empty((per, W, 3), dtype=torch.uint8, device="cuda") if world > 1 else None
 
@@ -240,7 +244,7 @@ def run_ours(args):
     def frame(gather=True):
         """One frame; with several GPUs: this rank's band, the chain hand-off, and the NCCL gather of the 8-bit bands."""
         with torch.cuda.stream(stream):
-            M.render_frame(r, rank, world, comm, band_out=(band.data_ptr(), band.numel()) if world > 1 else None)
+            M.render_frame(r, rank, world, comm, band_out=(band.data_ptr(), band.numel()) if world > 1 else None, peer=peer)
             if world > 1 and gather:
                 return M.gather_bands(dist, torch, band, H, W, world)
         return None
@@ -312,6 +316,8 @@ def run_ours(args):
     nprof = 3
     for _ in range(nprof):
         flush_l2()
+        if world > 1:
+            dist.barrier()  # keep the ranks within one frame of each other (the hand-off mailboxes hold 16 frames)
         frame(gather=False)
     fgl.sync()
     kern = fgl.timings()
@@ -360,7 +366,8 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "reference assets (obj/*) / procedural mesh, camera and light of the scene",
                 "config": {"workload": info["desc"], "triangles": info["triangles"], "width": info["out_w"], "height": info["out_h"],
-                           "partition": "sort-first row bands, %d rows per GPU, geometry replicated, RGB8 bands all-gathered with NCCL" % per if world > 1 else "single GPU",
+                           "partition": ("sort-first row bands, %d rows per GPU, geometry replicated, RGB8 bands all-gathered with NCCL, PCSS chain state handed on through %s"
+                                         % (per, "peer memory (device-side wait)" if peer else "the host (NCCL send/recv)")) if world > 1 else "single GPU",
                            "l2": "explicit 256 MiB flush between timed frames" if flush_buf is not None else "planes (%.0f MB per GPU) exceed the 126 MB L2" % (plane_bytes / 1e6)},
                 "frames_per_s": 1e3 / ms,
                 "e2e": {"value": out_px / 1e6 / (e2e_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": e2e_ms,
@@ -389,6 +396,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(SYNTH))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--handoff", default="peer", choices=["peer", "host"], help="N > 1, PCSS: how the chain state travels between the bands")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

@@ -234,6 +234,17 @@ class Fgl:
         self.call("fgl_draw_screen_space_pixels", (C.c_float * 3)(*eye), (C.c_float * 3)(*light_pos),
                   (C.c_float * 3)(*light_color))
 
+    # ---- device-side PCSS chain hand-off (sort-first groups)
+    def chain_peer_mailbox(self):
+        """(device pointer, 64-byte CUDA IPC handle) of this context's mailbox."""
+        ptr, h = C.c_void_p(), (C.c_uint8 * 64)()
+        self.call("fgl_chain_peer_mailbox", C.byref(ptr), h, C.c_size_t(64))
+        return ptr.value, bytes(h)
+
+    def chain_peer_connect(self, next_ptr=None, next_ipc=None, wait_prev=False, enable=True):
+        buf = (C.c_uint8 * 64).from_buffer_copy(next_ipc) if next_ipc else None
+        self.call("fgl_chain_peer_connect", C.c_void_p(next_ptr or 0), buf, int(wait_prev), int(enable))
+
     def prepare_screen_space_pixels(self, eye, light_pos, light_color):
         self.call("fgl_prepare_screen_space_pixels", (C.c_float * 3)(*eye), (C.c_float * 3)(*light_pos), (C.c_float * 3)(*light_color))
 

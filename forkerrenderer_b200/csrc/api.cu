@@ -545,6 +545,18 @@ int fgl_get_chain_blockers(fgl_ctx* c, uint64_t* out)
     *out = v;
     return FGL_OK;
 }
+int fgl_chain_peer_mailbox(fgl_ctx* c, void** device_ptr, void* ipc_handle, size_t ipc_handle_bytes)
+{
+    ENTER(c);
+    if (ipc_handle && ipc_handle_bytes < 64) return fgl_fail(c, FGL_ERR_INVALID, "fgl_chain_peer_mailbox: a CUDA IPC handle needs 64 bytes");
+    return fgl_stream_peer_mailbox(c, device_ptr, ipc_handle);
+}
+int fgl_chain_peer_connect(fgl_ctx* c, void* next_device_ptr, const void* next_ipc_handle, int wait_for_previous, int enable)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    return fgl_stream_peer_connect(c, next_device_ptr, next_ipc_handle, wait_for_previous, enable);
+}
 int fgl_set_row_band(fgl_ctx* c, int row0, int row1)
 {
     ENTER(c);

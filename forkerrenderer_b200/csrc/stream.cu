@@ -437,6 +437,7 @@ struct ChainRows
     const float2*             disk;
     double                    fs;
     unsigned long long        base;  // chunk of site i with k earlier blockers = base + i + 2 k
+    const unsigned long long* kDev;   // device-side hand-off: blockers found by the bands above (added to base as 2 k); NULL = none
     unsigned long long*       stats;  // diagnostics (FGL_CHAIN_STATS=1): pairs, decided-one, ambiguous, taps in E\F cells, warp tasks
 };
 
@@ -631,6 +632,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* 
         uint32_t*      GM = GMall + (size_t)(it & 1) * segsPerIter * W;
         int*           segLo = segLoAll + (size_t)(it & 1) * segsPerIter;
         const int      pre0 = __ldg(Ppre + j0);
+        const size_t   kBefore = R.kDev ? (size_t)*R.kDev : 0;  // written by k_peer_wait before this kernel started
         // Evaluation is balanced over the grid by interleaving ROWS: CTA b takes rows b, b + G, b + 2 G, ... (hard rows
         // come in runs along shadow edges; whole segments per CTA left most SMs waiting for a few).  Its local row
         // rr = 32 i + warp is super-chunk row t = (32 i + warp) * G + b.  Tables are per SEGMENT: CTA b builds the tables
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* 
             for (int i = 0; i < kMaxSpc; ++i)
             {
                 lo[i] = rowValid[i] ? max(0, lo[i] - pre0 - W / 2) : 0;
-                chunk0[i] = (size_t)R.base + upix[i] + 2 * ((size_t)uc1[i] + m0 + (size_t)lo[i]);
+                chunk0[i] = (size_t)R.base + 2 * kBefore + upix[i] + 2 * ((size_t)uc1[i] + m0 + (size_t)lo[i]);
 #pragma unroll
                 for (int h = 0; h < NW; ++h)
                 {
@@ -960,6 +962,53 @@ __global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* 
     }
 }
 
+// ---- device-side hand-off of the chain state between the bands of a sort-first group ----------------------------------
+// Band r + 1 needs the number of blockers found in bands 0..r.  Instead of a host round trip per band (stream sync, NCCL
+// send / recv, launch), the contexts exchange it through peer memory over NVLink: every context owns a mailbox of 16
+// (epoch, value) slots; k_peer_notify of band r stores its running total into band r + 1's mailbox (value, system
+// fence, epoch), k_peer_wait of band r + 1 — queued on its stream in front of the chain kernel — spins on the slot of
+// the current frame.  A 30 s time-out turns a missing neighbour into an error instead of a hang.
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_peer_wait(const unsigned long long* mailbox, unsigned long long epoch, unsigned long long* kDev, unsigned* err)
+{
+    const unsigned long long* slot = mailbox + (epoch & 15ull) * 2;
+    const unsigned long long  t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(slot) != epoch)
+    {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > 30000000000ull)
+        {
+            *err = 1u, *kDev = 0ull;
+            return;
+        }
+    }
+    *kDev = ld_acquire_sys_u64(slot + 1);
+}
+__global__ void k_peer_notify(unsigned long long* nextMailbox, unsigned long long epoch, const unsigned long long* kDev, const unsigned* state,
+                              unsigned long long hostBefore, unsigned nC1, int hasChain, unsigned long long* totalOut)
+{
+    unsigned long long total = hostBefore + (kDev ? *kDev : 0ull) + nC1 + (hasChain ? (unsigned long long)state[CH_M0] : 0ull);
+    *totalOut = total;
+    if (nextMailbox)
+    {
+        unsigned long long* slot = nextMailbox + (epoch & 15ull) * 2;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(total) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(epoch) : "memory");
+    }
+}
+
 __global__ void __launch_bounds__(256) k_pixel_flags(size_t n, const int* isU, const int* isC1, const int* posU, const uint8_t* flagU, int* hasBlocker)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -985,10 +1034,11 @@ struct DeepShadow
     float        areaLight;
 };
 __global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long long base, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis,
-                                                     unsigned* blockerList, unsigned* nBlockers, DeepShadow D)
+                                                     unsigned* blockerList, unsigned* nBlockers, DeepShadow D, const unsigned long long* kDev)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
+    if (kDev) base += 2ull * *kDev;
     chunkOf[idx] = (unsigned)(base + idx + 2ull * (unsigned)kpre[idx]);
     float v = 1.f;
     if (hasB[idx])
@@ -1114,6 +1164,12 @@ struct SampleStream
     DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
     DevBuf sig, vis, blockerList, pilot, Ppre, winLo, chainStats, rowBits;
     unsigned long long sigChunks = 0;
+    // device-side hand-off (peer mailboxes)
+    DevBuf              mailbox, peerLocal;  // 16 x (epoch, value); {kDev, total, err}
+    unsigned long long* nextMailbox = nullptr;
+    void*               nextMailboxIpc = nullptr;  // mapping to close
+    bool                peerOn = false, peerWait = false, peerTotalOnDevice = false;
+    unsigned long long  peerEpoch = 0;
     // FGL_VIS_PREPARE -> FGL_VIS_RESOLVE hand-over
     bool               prepValid = false;
     size_t             prepTotal = 0, prepLo = 0, prepHi = 0;
@@ -1132,6 +1188,9 @@ void fgl_stream_destroy(fgl_ctx* c)
 {
     SampleStream* s = c->stream_state;
     if (!s) return;
+    if (s->nextMailboxIpc) cudaIpcCloseMemHandle(s->nextMailboxIpc);
+    if (s->mailbox.p) cudaFree(s->mailbox.p);
+    if (s->peerLocal.p) cudaFree(s->peerLocal.p);
     DevBuf* all[] = { &s->ckpt, &s->window, &s->tileCounts, &s->tileOffsets, &s->counters, &s->ball, &s->disk, &s->smTmpMin, &s->smTmpMax, &s->smMin,
                       &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->pilot, &s->Ppre, &s->winLo, &s->chainStats, &s->rowBits, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
                       &s->chunkOf, &s->mState };
@@ -1145,6 +1204,7 @@ void fgl_stream_begin_frame(fgl_ctx* c)
 {
     SampleStream* s = S_of(c);
     s->prepValid = false;
+    if (s->peerOn) ++s->peerEpoch;
     s->ssaoThisFrame = false;
     s->ssaoSamples = 0;
 }
@@ -1421,6 +1481,18 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     }
     unsigned long long uncertainBlockers = 0;
     c->lastUncertain = nU;
+    R.kDev = nullptr;
+    if (s->peerOn)
+    {   // blockers of the bands above arrive in this context's mailbox; rank 0 of the group (peerWait off) starts from zero
+        unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
+        R.kDev = loc;
+        if (s->peerWait)
+        {
+            LaunchScope ls(c, "pcss_peer_wait", 0);
+            k_peer_wait<<<1, 1, 0, st>>>((const unsigned long long*)s->mailbox.p, s->peerEpoch, loc, (unsigned*)(loc + 2));
+        }
+        else FGL_CUDA(c, cudaMemsetAsync(loc, 0, 8, st));
+    }
     if (nU > 0)
     {
         R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
@@ -1475,6 +1547,12 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
                     hq[0], hq[1], hq[2], hq[3]);
         }
     }
+    if (s->peerOn)
+    {
+        unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
+        LaunchScope         ls(c, "pcss_peer_notify", 0);
+        k_peer_notify<<<1, 1, 0, st>>>(s->nextMailbox, s->peerEpoch, loc, (const unsigned*)s->mState.p, blockersBefore, (unsigned)nC1, nU > 0 ? 1 : 0, loc + 1);
+    }
     {
         LaunchScope ls(c, "pcss_flags", n * 16);
         k_pixel_flags<<<nb, 256, 0, st>>>(n, (const int*)s->isU.p, (const int*)s->isC1.p, (const int*)s->posU.p, (const uint8_t*)s->flagU.p, (int*)s->hasB.p);
@@ -1486,7 +1564,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         D.isC1 = (const int*)s->isC1.p, D.sc4 = sc4In, D.smMin = (const float*)s->smMin.p, D.smMax = (const float*)s->smMax.p, D.sm = L.sm, D.r = r;
         D.pcfFilter = L.pcfFilter, D.areaLight = L.areaLight;
         k_chunk_index<<<nb, 256, 0, st>>>(n, chunkBase, (const int*)s->kpre.p, (const int*)s->hasB.p, chunkOfB, visB, (unsigned*)s->blockerList.p,
-                                          (unsigned*)s->mState.p + CH_NBLOCKERS, D);
+                                          (unsigned*)s->mState.p + CH_NBLOCKERS, D, R.kDev);
     }
     {
         LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
@@ -1497,6 +1575,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     // known on the host as soon as the chain kernel has finished — a sort-first driver can hand it to the next band while
     // this band's filter and lighting kernels are still running
     s->chainTotal = blockersBefore + (unsigned long long)nC1 + uncertainBlockers, s->chainCountValid = true;
+    s->peerTotalOnDevice = s->peerOn;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fgl_fail(c, FGL_ERR_CUDA, std::string("pcss chain: ") + cudaGetErrorString(e));
     return FGL_OK;
@@ -1526,11 +1605,64 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase)
     return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, lo, hi, c->chainBlockersBefore, phase);
 }
 
-// Blockers found up to and including this context's band (= input of the next band's chain).  Does not touch the stream.
+// Blockers found up to and including this context's band (= input of the next band's chain).  Host hand-off: known without
+// touching the stream; device-side hand-off: the running total lives on the device (blocks on the stream).
 int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out)
 {
     SampleStream* s = S_of(c);
     if (!s->chainCountValid) return fgl_fail(c, FGL_ERR_STATE, "no PCSS chain has run on this context");
     *out = s->chainTotal;
+    if (s->peerTotalOnDevice)
+    {
+        unsigned long long v[3] = { 0, 0, 0 };
+        FGL_CUDA(c, cudaMemcpyAsync(v, s->peerLocal.p, 24, cudaMemcpyDeviceToHost, c->stream));
+        FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (v[2]) return fgl_fail(c, FGL_ERR_STATE, "PCSS chain hand-off: the band above never signalled (30 s)");
+        *out = v[1];
+    }
+    return FGL_OK;
+}
+
+// ---- peer hand-off set-up ---------------------------------------------------------------------------------------------
+static int peer_buffers(fgl_ctx* c, SampleStream* s)
+{
+    if (s->mailbox.p) return FGL_OK;
+    if (int rc = fgl_reserve(c, s->mailbox, 16 * 2 * 8)) return rc;
+    if (int rc = fgl_reserve(c, s->peerLocal, 64)) return rc;
+    FGL_CUDA(c, cudaMemset(s->mailbox.p, 0, 16 * 2 * 8));
+    FGL_CUDA(c, cudaMemset(s->peerLocal.p, 0, 64));
+    return FGL_OK;
+}
+int fgl_stream_peer_mailbox(fgl_ctx* c, void** devPtr, void* ipcHandle64)
+{
+    SampleStream* s = S_of(c);
+    if (int rc = peer_buffers(c, s)) return rc;
+    if (devPtr) *devPtr = s->mailbox.p;
+    if (ipcHandle64)
+    {
+        cudaIpcMemHandle_t h;
+        FGL_CUDA(c, cudaIpcGetMemHandle(&h, s->mailbox.p));
+        static_assert(sizeof h == 64, "CUDA IPC handles are 64 bytes");
+        memcpy(ipcHandle64, &h, 64);
+    }
+    return FGL_OK;
+}
+int fgl_stream_peer_connect(fgl_ctx* c, void* nextDevPtr, const void* nextIpcHandle64, int waitPrev, int enable)
+{
+    SampleStream* s = S_of(c);
+    if (s->nextMailboxIpc) cudaIpcCloseMemHandle(s->nextMailboxIpc), s->nextMailboxIpc = nullptr;
+    s->nextMailbox = nullptr, s->peerOn = false, s->peerWait = false;
+    if (!enable) return FGL_OK;
+    if (int rc = peer_buffers(c, s)) return rc;
+    if (nextIpcHandle64)
+    {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, nextIpcHandle64, 64);
+        void* p = nullptr;
+        FGL_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->nextMailboxIpc = p, s->nextMailbox = (unsigned long long*)p;
+    }
+    else s->nextMailbox = (unsigned long long*)nextDevPtr;
+    s->peerOn = true, s->peerWait = waitPrev != 0, s->peerEpoch = 0;
     return FGL_OK;
 }

@@ -17,3 +17,6 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase = FGL_VIS_AL
 int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t n, const float4* sc4, size_t siteLo, size_t siteHi, unsigned long long blockersBefore,
                                int phase = FGL_VIS_ALL);
 int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out);
+// Device-side hand-off of the chain state through peer memory (include/forkergl_b200.h: fgl_chain_peer_*)
+int fgl_stream_peer_mailbox(fgl_ctx* c, void** devPtr, void* ipcHandle64);
+int fgl_stream_peer_connect(fgl_ctx* c, void* nextDevPtr, const void* nextIpcHandle64, int waitPrev, int enable);

@@ -46,20 +46,52 @@ class SyntheticRenderer:
         self.scene.render_finish()
 
 
-def render_frame(r, rank, world, comm=None, band_out=None):
+def setup_peer_handoff(fgl, dist, rank, world, height):
+    """Connects the contexts of a sort-first group for the DEVICE-side chain hand-off (fgl_chain_peer_*): every rank
+    publishes the CUDA IPC handle of its mailbox, opens the next rank's, and from then on waits / signals inside its
+    own stream.  Returns False (and leaves the host hand-off in place) if a band would be empty or IPC is not available."""
+    if world < 2 or band_rows(height, world, world - 1)[1] <= band_rows(height, world, world - 1)[0]:
+        return False
+    ok = True
+    try:
+        _, handle = fgl.chain_peer_mailbox()
+    except Exception:
+        handle, ok = None, False
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    if not ok or any(h is None for h in handles):
+        return False
+    try:
+        fgl.chain_peer_connect(next_ipc=handles[rank + 1] if rank + 1 < world else None, wait_prev=rank > 0)
+    except Exception:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        fgl.chain_peer_connect(enable=False)
+        return False
+    return True
+
+
+def render_frame(r, rank, world, comm=None, band_out=None, peer=False):
     """One frame of renderer `r` on this rank's band.  `comm` needs send_int(value, dst) / recv_int(src) when world > 1
-    and the frame has a PCSS chain.  If band_out (a device pointer, bytes) is given, the band's RGB8 rows are copied
-    there on the library's stream.  Returns (r0, r1)."""
+    and the frame has a PCSS chain, unless the contexts were connected with setup_peer_handoff (peer=True: the chain
+    state travels between the GPUs' streams without the host).  If band_out (a device pointer, bytes) is given, the
+    band's RGB8 rows are copied there on the library's stream.  Returns (r0, r1)."""
     r0, r1, per = band_rows(r.height, world, rank)
     r.begin((r0, r1))
-    if r.pcss:
+    if r.pcss and peer:
+        r.finish()
+    elif r.pcss:
         k = 0
         if world > 1 and rank > 0 and r1 > r0:
             k = comm.recv_int(rank - 1)
         r.fgl.set_chain_blockers_before(k)
-    r.finish()
-    if r.pcss and world > 1 and rank < world - 1:
-        comm.send_int(r.fgl.get_chain_blockers() if r1 > r0 else 0, rank + 1)
+        r.finish()
+        if world > 1 and rank < world - 1:
+            comm.send_int(r.fgl.get_chain_blockers() if r1 > r0 else 0, rank + 1)
+    else:
+        r.finish()
     if band_out is not None and r1 > r0:
         ptr, nbytes = band_out
         r.fgl.copy_plane_rows_to_device(11, r0, r1, ptr, (r1 - r0) * r.width * 3)  # FGL_PLANE_FRAME_RGB8

@@ -177,6 +177,17 @@ int fgl_begin_frame(fgl_ctx* ctx);
  * buffer rows [row_begin, row_end) (plus the few halo rows SSAO and the blur recurrence need).  The shadow pass and
  * the camera depth plane always cover the whole buffer (SSAO gathers depth anywhere).  (0, -1) = everything. */
 int fgl_set_row_band(fgl_ctx* ctx, int row_begin, int row_end);
+/* Device-side hand-off of the PCSS chain state inside a sort-first group on one NVLink / NVSwitch box (one context per
+ * GPU, usually one process per GPU).  Every context owns a mailbox in device memory; the context of band r + 1 waits
+ * ON THE DEVICE (a one-thread kernel queued in front of its chain kernel) for the running blocker count that the
+ * context of band r stores into it by a peer write when its own chain kernel has finished — no host round trip, no
+ * fgl_set_chain_blockers_before / fgl_get_chain_blockers per band.
+ *   fgl_chain_peer_mailbox: this context's mailbox as a device pointer (same process) and / or as a 64-byte CUDA IPC handle.
+ *   fgl_chain_peer_connect: the NEXT band's mailbox (pointer, or IPC handle from another process; both NULL for the last
+ *   band), whether this band waits for a previous one (0 for the first band), enable = 0 switches the mechanism off.
+ * Frames are counted from the connect call; all contexts of the group must render the same sequence of frames. */
+int fgl_chain_peer_mailbox(fgl_ctx* ctx, void** out_device_ptr, void* out_ipc_handle, size_t ipc_handle_bytes);
+int fgl_chain_peer_connect(fgl_ctx* ctx, void* next_device_ptr, const void* next_ipc_handle, int wait_for_previous, int enable);
 /* Sort-first PCSS: the sample-stream position of a band depends on how many pixels of the bands before it found a
  * blocker (shadow.cpp:96-105).  Set that count before the lighting pass of a band; read the running total (count
  * before + this band's) after it and hand it to the next band.  Both default to / start from 0 for a whole frame. */

@@ -40,3 +40,28 @@ def test_bands_equal_full_frame(mode, ssao, world, gpu_fgl):
     finally:
         for f in ctxs:
             f.close()
+
+
+@pytest.mark.parametrize("ssao,world", [(True, 2), (False, 4)])
+def test_bands_with_device_side_handoff(ssao, world, gpu_fgl):
+    """The same, with the chain state travelling through the contexts' mailboxes (fgl_chain_peer_*: a peer store from the
+    band above, a device-side wait in front of the chain kernel) instead of the host — two frames, to cover the epochs."""
+    W, H = 320, 240
+    full_scene = SyntheticScene(gpu_fgl, quads=40)
+    full_scene.render(W, H, shadow_mode=B.SHADOW_PCSS, ssao=ssao)
+    full = gpu_fgl.read_plane("frame_u8")
+    ctxs = [B.product_fgl(0) for _ in range(world)]
+    try:
+        boxes = [f.chain_peer_mailbox()[0] for f in ctxs]
+        for rank, f in enumerate(ctxs):
+            f.chain_peer_connect(next_ptr=boxes[rank + 1] if rank + 1 < world else None, wait_prev=rank > 0)
+        renderers = [M.SyntheticRenderer(SyntheticScene(f, quads=40), W, H, shadow_mode=B.SHADOW_PCSS, ssao=ssao) for f in ctxs]
+        for frame in range(2):
+            for rank, (f, r) in enumerate(zip(ctxs, renderers)):
+                r0, r1 = M.render_frame(r, rank, world, None, peer=True)
+                got = f.read_plane("frame_u8")
+                assert np.array_equal(got[r0:r1], full[r0:r1]), "frame %d: band %d of %d differs from the full frame" % (frame, rank, world)
+        assert ctxs[-1].get_chain_blockers() == gpu_fgl.get_chain_blockers()
+    finally:
+        for f in ctxs:
+            f.close()
