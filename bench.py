@@ -278,7 +278,8 @@ def run_ours(args):
     d2h = 0
     frame_hash = None
     host_frame = None  # page-locked destination of the gathered frame (rank 0)
-    for i in range(args.steps + 1):
+    E2E_WARM = 2  # untimed passes: the first one allocates the page-locked frame buffer and fingerprints the frame
+    for i in range(args.steps + E2E_WARM):
         flush_l2()
         if world > 1:
             dist.barrier()
@@ -289,6 +290,9 @@ def run_ours(args):
             if rank == 0:
                 if host_frame is None:
                     host_frame = torch.empty(full.shape, dtype=torch.uint8, pin_memory=True)
+                if os.environ.get("FGL_BENCH_DEBUG"):
+                    stream.synchronize()
+                    _dbg("e2e step %d: frame + gather %.3f ms" % (i, 1e3 * (time.perf_counter() - t0)))
                 with torch.cuda.stream(stream):
                     host_frame.copy_(full, non_blocking=True)
                 stream.synchronize()
@@ -300,9 +304,10 @@ def run_ours(args):
             img = fgl.read_plane("ssaa_u8" if info["ssaa"] else "frame_u8", pinned=True)  # page-locked host buffer (fgl_host_alloc)
             d2h = int(img.nbytes)
         t1 = time.perf_counter()
-        if i:
+        _dbg("e2e step %d: %.3f ms" % (i, 1e3 * (t1 - t0)))
+        if i >= E2E_WARM:
             e2e_t.append(t1 - t0)
-        elif rank == 0:  # the untimed first pass: fingerprint of the finished frame (must not depend on the number of GPUs)
+        elif i == 0 and rank == 0:  # the untimed first pass: fingerprint of the finished frame (must not depend on the number of GPUs)
             import hashlib
             frame_hash = hashlib.sha256(np.ascontiguousarray(img.numpy() if hasattr(img, "numpy") else img).tobytes()).hexdigest()
     e2e_ms = 1e3 * sum(e2e_t) / len(e2e_t)
