@@ -76,7 +76,7 @@ int plane_init(fgl_ctx* c, int plane, int w, int h, float value)
     PlaneH& p = c->planes[plane];
     p.w = w, p.h = h, p.ch = is1ch(plane) ? 1 : 3;
     if (int rc = fgl_reserve(c, p.buf, (size_t)w * h * p.ch * 4)) return rc;
-    p.fillPending = true, p.fillValue = value, p.fillIsRGB = false;
+    p.fillPending = true, p.fillValue = value, p.fillIsRGB = false, p.fillPartial = false;
     return FGL_OK;
 }
 
@@ -87,8 +87,28 @@ int materialize(fgl_ctx* c, int plane)
     if (!p.fillPending || !p.buf.p) return FGL_OK;
     p.fillPending = false;
     size_t n = (size_t)p.w * p.h;
+    if (p.fillPartial)
+    {   // a band's passes wrote rows [validRow0, validRow1): clear the rest, channel by channel (SoA)
+        p.fillPartial = false;
+        for (int ch = 0; ch < p.ch; ++ch)
+        {
+            float* base = (float*)p.buf.p + (size_t)ch * n;
+            float  v = p.fillIsRGB ? p.fillRGB[ch] : p.fillValue;
+            if (int rc = fgl_run_fill(c, base, (size_t)p.validRow0 * p.w, v)) return rc;
+            if (int rc = fgl_run_fill(c, base + (size_t)p.validRow1 * p.w, (size_t)(p.h - p.validRow1) * p.w, v)) return rc;
+        }
+        return FGL_OK;
+    }
     if (p.fillIsRGB) return fgl_run_fill_rgb(c, (float*)p.buf.p, n, p.fillRGB);
     return fgl_run_fill(c, (float*)p.buf.p, n * p.ch, p.fillValue);
+}
+
+// The kernels of a band only touch rows [r0, r1): nothing to clear if the band's own passes wrote them.
+int materialize_rows(fgl_ctx* c, int plane, int r0, int r1)
+{
+    PlaneH& p = c->planes[plane];
+    if (p.fillPending && p.fillPartial && r0 >= p.validRow0 && r1 <= p.validRow1) return FGL_OK;
+    return materialize(c, plane);
 }
 
 void band_of(fgl_ctx* c, int H, int& r0, int& r1)
@@ -221,8 +241,13 @@ int flush(fgl_ctx* c)
                 c->flushedPrims = c->primCounter;
                 return fgl_fail(c, FGL_ERR_STATE, "geometry pass without InitGeometryBuffers of the depth buffer's size");
             }
-            if (fullBand) c->planes[pl].fillPending = false;
-            else if (int rc = materialize(c, pl)) return rc;
+            PlaneH& w = c->planes[pl];
+            if (fullBand || pl == FGL_PLANE_DEPTH) w.fillPending = false, w.fillPartial = false;  // the resolve writes every depth texel, band or not
+            else if (w.fillPending && !w.fillPartial) w.fillPartial = true, w.validRow0 = P.row0, w.validRow1 = P.row1;  // clear of the other rows deferred
+            else if (w.fillPending && (w.validRow0 != P.row0 || w.validRow1 != P.row1))
+            {
+                if (int rc = materialize(c, pl)) return rc;
+            }
         }
     }
     else if (c->pass == FGL_PASS_FORWARD)
@@ -614,18 +639,19 @@ static int build_light_pass(fgl_ctx* c, const float eye[3], const float lpos[3],
     {
         const PlaneH& q = c->planes[pl];
         if (!q.buf.p || q.w != frame.w || q.h != frame.h) return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels: G-buffers missing or of another size");
-        if (int rc = materialize(c, pl)) return rc;
     }
     memset(&L, 0, sizeof L);
     L.W = frame.w, L.H = frame.h;
     band_of(c, L.H, L.row0, L.row1);
+    for (int pl : inputs)
+        if (int rc = materialize_rows(c, pl, L.row0, L.row1)) return rc;
     fill_light_consts(c, L);
     if (c->shadowOn)
     {
         const PlaneH& q = c->planes[FGL_PLANE_LIGHTNDC];
         if (!q.buf.p || q.w != frame.w || q.h != frame.h || !c->planes[FGL_PLANE_SHADOW].buf.p)
             return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels: shadows on without LightSpaceNDCPosGBuffer / ShadowBuffer");
-        if (int rc = materialize(c, FGL_PLANE_LIGHTNDC)) return rc;
+        if (int rc = materialize_rows(c, FGL_PLANE_LIGHTNDC, L.row0, L.row1)) return rc;
         if (int rc = materialize(c, FGL_PLANE_SHADOW)) return rc;
         L.sm = shadow_map_dev(c);
     }
@@ -683,12 +709,13 @@ int fgl_ssao(fgl_ctx* c)
     {
         const PlaneH& q = c->planes[pl];
         if (!q.buf.p || q.w != frame.w || q.h != frame.h) return fgl_fail(c, FGL_ERR_STATE, "SSAO: G-buffers missing or of another size");
-        if (int rc = materialize(c, pl)) return rc;
     }
     SsaoPass S;
     memset(&S, 0, sizeof S);
     S.W = frame.w, S.H = frame.h;
     halo_band_of(c, S.H, S.row0, S.row1);
+    for (int pl : inputs)
+        if (int rc = pl == FGL_PLANE_DEPTH ? materialize(c, pl) : materialize_rows(c, pl, S.row0, S.row1)) return rc;  // depth is gathered from anywhere
     S.worldpos = (const float*)c->planes[FGL_PLANE_WORLDPOS].buf.p, S.normal = (const float*)c->planes[FGL_PLANE_NORMAL].buf.p;
     S.depth = (const float*)dp.buf.p, S.ao = (float*)c->planes[FGL_PLANE_AO].buf.p;
     memcpy(S.viewProj, c->viewProj, 64), memcpy(S.viewport, c->viewport, 64);
@@ -705,10 +732,10 @@ int fgl_blur(fgl_ctx* c, int plane, int kind)
     if (int rc = flush(c)) return rc;
     PlaneH& p = c->planes[plane];
     if (!p.buf.p) return fgl_fail(c, FGL_ERR_STATE, "fgl_blur: plane not initialised");
-    if (int rc = materialize(c, plane)) return rc;
     if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = false;
     int h0, h1, v0, v1;
     halo_band_of(c, p.h, h0, h1);
+    if (int rc = kind == FGL_BLUR_TWO_PASS_GAUSSIAN ? materialize_rows(c, plane, h0, h1) : materialize(c, plane)) return rc;
     band_of(c, p.h, v0, v1);
     v0 = std::max(0, v0 - kBlurWarm);
     return fgl_run_blur(c, (float*)p.buf.p, p.w, p.h, p.ch, kind, h0, h1, v0, v1);

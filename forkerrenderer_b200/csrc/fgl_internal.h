@@ -93,6 +93,10 @@ struct PlaneH
     float  fillValue = 0.f;
     float  fillRGB[3] = { 0, 0, 0 };
     bool   fillIsRGB = false;
+    // sort-first bands: rows [validRow0, validRow1) were written by this band's passes; only the others still need the clear
+    // value, and only if somebody reads them (a host read of the whole plane) — fillPending stays set until then
+    bool   fillPartial = false;
+    int    validRow0 = 0, validRow1 = 0;
 };
 
 struct TextureH

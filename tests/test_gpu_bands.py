@@ -65,3 +65,23 @@ def test_bands_with_device_side_handoff(ssao, world, gpu_fgl):
     finally:
         for f in ctxs:
             f.close()
+
+
+def test_band_planes_read_back_cleared_outside_the_band(gpu_fgl):
+    """A band's passes only write their own rows (+ halo); the clear of the other rows is deferred until somebody reads the
+    plane — a host read must still see the reference's clear values there, and the band's rows of the full render."""
+    W, H, world, rank = 320, 240, 3, 1
+    SyntheticScene(gpu_fgl, quads=40).render(W, H, shadow_mode=B.SHADOW_HARD, ssao=True)
+    full = {k: gpu_fgl.read_plane(k) for k in ("normal", "albedo", "ao", "depth")}
+    f = B.product_fgl(0)
+    try:
+        r = M.SyntheticRenderer(SyntheticScene(f, quads=40), W, H, shadow_mode=B.SHADOW_HARD, ssao=True)
+        r0, r1 = M.render_frame(r, rank, world, None)
+        for k, clear in (("normal", 0.0), ("albedo", 0.0), ("ao", 1.0)):
+            got = f.read_plane(k)
+            assert np.array_equal(got[r0:r1], full[k][r0:r1]), k
+            lo, hi = max(0, r0 - 64), min(H, r1 + 4)  # halo rows hold band-local data
+            assert np.all(got[:lo] == clear) and np.all(got[hi:] == clear), k
+        assert np.array_equal(f.read_plane("depth"), full["depth"])  # SSAO gathers depth from anywhere: resolved everywhere
+    finally:
+        f.close()
