@@ -245,8 +245,9 @@ class Fgl:
         buf = (C.c_uint8 * 64).from_buffer_copy(next_ipc) if next_ipc else None
         self.call("fgl_chain_peer_connect", C.c_void_p(next_ptr or 0), buf, int(wait_prev), int(enable))
 
-    def prepare_screen_space_pixels(self, eye, light_pos, light_color):
-        self.call("fgl_prepare_screen_space_pixels", (C.c_float * 3)(*eye), (C.c_float * 3)(*light_pos), (C.c_float * 3)(*light_color))
+    def prepare_screen_space_pixels(self, eye, light_pos, light_color, ssao_follows):
+        self.call("fgl_prepare_screen_space_pixels", (C.c_float * 3)(*eye), (C.c_float * 3)(*light_pos), (C.c_float * 3)(*light_color),
+                  int(bool(ssao_follows)))
 
     # ---- buffers
     def plane_info(self, plane):

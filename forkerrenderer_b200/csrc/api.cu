@@ -358,7 +358,9 @@ void fgl_destroy(fgl_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->chainStream) cudaStreamSynchronize(c->chainStream);
     cudaStreamSynchronize(c->stream);
+    if (c->chainStream) cudaStreamDestroy(c->chainStream), cudaEventDestroy(c->evChainGo), cudaEventDestroy(c->evChainDone);
     fgl_stream_destroy(c);
     for (auto& p : c->planes) release(p.buf);
     release(c->frameRgb8), release(c->ssaaRgb8), release(c->visCamera), release(c->visLight), release(c->texTable);
@@ -395,6 +397,7 @@ int fgl_sync(fgl_ctx* c)
 {
     ENTER(c);
     if (int rc = flush(c)) return rc;
+    if (c->chainStream) FGL_CUDA(c, cudaStreamSynchronize(c->chainStream));
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
     return FGL_OK;
 }
@@ -552,6 +555,11 @@ int fgl_begin_frame(fgl_ctx* c)
 {
     ENTER(c);
     if (int rc = flush(c)) return rc;
+    if (c->chainEventPending)
+    {   // a chain that nobody picked up: the new frame's passes must not overtake it
+        FGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->evChainDone, 0));
+        c->chainEventPending = false;
+    }
     fgl_stream_begin_frame(c);
     return FGL_OK;
 }
@@ -664,13 +672,41 @@ static int build_light_pass(fgl_ctx* c, const float eye[3], const float lpos[3],
 // Optional first half of fgl_draw_screen_space_pixels: everything of a PCSS frame that does not depend on the bands above
 // this one (shadow coordinates, min/max maps, classification, cell masks, the pilot).  A sort-first driver calls it
 // before it waits for the previous band's blocker count; single-GPU callers never need it.
-int fgl_prepare_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3])
+int fgl_prepare_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3], int ssao_follows)
 {
     ENTER(c);
     LightPass L;
     bool      fullBand = false;
     if (int rc = build_light_pass(c, eye, lpos, lcol, L, fullBand)) return rc;
-    if (c->shadowOn && c->params.shadow_mode == FGL_SHADOW_PCSS) return fgl_stream_prepare_lighting(c, L, FGL_VIS_PREPARE);
+    if (!(c->shadowOn && c->params.shadow_mode == FGL_SHADOW_PCSS)) return FGL_OK;
+    if (ssao_follows)
+    {   // SSAO consumes the sample stream first (render.cpp:204-209): the lighting phase starts where its 32 samples per pixel end
+        SsaoPass S;
+        memset(&S, 0, sizeof S);
+        S.W = L.W, S.H = L.H;
+        if (int rc = fgl_stream_prepare_ssao(c, S)) return rc;
+    }
+    if (int rc = fgl_stream_prepare_lighting(c, L, FGL_VIS_PREPARE)) return rc;
+    // The chain itself can be issued right away when its input is known: a whole-frame context (nothing above it), or a
+    // band whose input arrives on the device (fgl_chain_peer_connect).  It goes to its own stream, behind an event, so
+    // that whatever the caller queues next on the main stream — SSAO, the blur — runs concurrently with it.
+    static const bool noOverlap = getenv("FGL_NO_CHAIN_OVERLAP") != nullptr;
+    if (noOverlap || !(fullBand || fgl_stream_peer_on(c))) return FGL_OK;
+    if (!c->chainStream)
+    {
+        FGL_CUDA(c, cudaStreamCreateWithFlags(&c->chainStream, cudaStreamNonBlocking));
+        FGL_CUDA(c, cudaEventCreateWithFlags(&c->evChainGo, cudaEventDisableTiming));
+        FGL_CUDA(c, cudaEventCreateWithFlags(&c->evChainDone, cudaEventDisableTiming));
+    }
+    FGL_CUDA(c, cudaEventRecord(c->evChainGo, c->stream));
+    FGL_CUDA(c, cudaStreamWaitEvent(c->chainStream, c->evChainGo, 0));
+    cudaStream_t mainStream = c->stream;
+    c->stream = c->chainStream;
+    int rc = fgl_stream_prepare_lighting(c, L, FGL_VIS_LAUNCH);
+    c->stream = mainStream;
+    if (rc) return rc;
+    FGL_CUDA(c, cudaEventRecord(c->evChainDone, c->chainStream));
+    c->chainEventPending = true;
     return FGL_OK;
 }
 
@@ -689,6 +725,11 @@ int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpo
     size_t n = (size_t)L.W * L.H;
     if (int rc = fgl_reserve(c, c->frameRgb8, n * 3 + 16)) return rc;
     L.rgb8 = (uint8_t*)c->frameRgb8.p;
+    if (c->chainEventPending)
+    {   // a chain issued by fgl_prepare_screen_space_pixels: everything from here on is ordered behind it
+        FGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->evChainDone, 0));
+        c->chainEventPending = false;
+    }
     if (c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD)
         if (int rc = fgl_stream_prepare_lighting(c, L, FGL_VIS_RESOLVE)) return rc;  // continues a prepared chain, else does it all
     if (int rc = fgl_run_lighting(c, L)) return rc;

@@ -129,6 +129,10 @@ struct fgl_ctx
     int          device = 0;
     std::string  error;
     cudaStream_t ownStream = nullptr, stream = nullptr;
+    // the PCSS chain kernel runs on its own stream so that SSAO and the blur (main stream) overlap it
+    cudaStream_t chainStream = nullptr;
+    cudaEvent_t  evChainGo = nullptr, evChainDone = nullptr;
+    bool         chainEventPending = false;
     FglParams    params;
     float        viewport[16], viewProj[16], lightSpace[16];
     int          mode = FGL_MODE_FORWARD, pass = FGL_PASS_FORWARD, shadowOn = 1;

@@ -1171,7 +1171,8 @@ struct SampleStream
     bool                peerOn = false, peerWait = false, peerTotalOnDevice = false;
     unsigned long long  peerEpoch = 0;
     // FGL_VIS_PREPARE -> FGL_VIS_RESOLVE hand-over
-    bool               prepValid = false;
+    bool               prepValid = false, chainInFlight = false;
+    unsigned long long inflightBefore = 0;
     size_t             prepTotal = 0, prepLo = 0, prepHi = 0;
     int                prepNU = 0, prepNC1 = 0;
     unsigned long long chainTotal = 0;  // blockers found up to and including this context's band
@@ -1203,7 +1204,7 @@ void fgl_stream_destroy(fgl_ctx* c)
 void fgl_stream_begin_frame(fgl_ctx* c)
 {
     SampleStream* s = S_of(c);
-    s->prepValid = false;
+    s->prepValid = false, s->chainInFlight = false;
     if (s->peerOn) ++s->peerEpoch;
     s->ssaoThisFrame = false;
     s->ssaoSamples = 0;
@@ -1351,7 +1352,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     P.sm = L.sm;
     if (!pcss)
     {
-        if (phase == FGL_VIS_PREPARE) return FGL_OK;  // PCF offsets are closed-form: nothing depends on earlier bands
+        if (phase == FGL_VIS_PREPARE || phase == FGL_VIS_LAUNCH) return FGL_OK;  // PCF offsets are closed-form: nothing depends on earlier bands
         size_t      nSites = siteHi - siteLo;
         LaunchScope ls(c, "pcf_visibility", nSites * (16 + 512 + 4));
         if (nSites) k_pcf_visibility<<<(unsigned)((nSites * 32 + 255) / 256), 256, 0, st>>>(L.sm, siteLo, siteHi, sc4All, L.disk, (float)L.pcfFilter, (float*)s->vis.p);
@@ -1383,7 +1384,10 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     int      nU = 0, nC1 = 0;  // uncertain sites; sites whose every tap blocks
     // Everything up to the pilot's prefix sums is independent of the blockers found in earlier bands: a sort-first
     // driver runs it (FGL_VIS_PREPARE) while it waits for the previous band's count, then resolves (FGL_VIS_RESOLVE).
-    const bool prepared = phase == FGL_VIS_RESOLVE && s->prepValid && s->prepTotal == nTotal && s->prepLo == siteLo && s->prepHi == siteHi;
+    const bool prepared = (phase == FGL_VIS_RESOLVE || phase == FGL_VIS_LAUNCH) && s->prepValid && s->prepTotal == nTotal && s->prepLo == siteLo && s->prepHi == siteHi;
+    // the chain may already be running (or finished) on its own stream: FGL_VIS_LAUNCH issued it, FGL_VIS_RESOLVE picks it up
+    const bool inflight = phase == FGL_VIS_RESOLVE && prepared && s->chainInFlight && s->inflightBefore == blockersBefore;
+    s->chainInFlight = false;
     if (prepared) nU = s->prepNU, nC1 = s->prepNC1;
     s->prepValid = false;
     ChainRows R;
@@ -1481,11 +1485,12 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     }
     unsigned long long uncertainBlockers = 0;
     c->lastUncertain = nU;
-    R.kDev = nullptr;
+    R.kDev = s->peerOn ? (const unsigned long long*)s->peerLocal.p : nullptr;
+    if (!inflight)
+    {
     if (s->peerOn)
     {   // blockers of the bands above arrive in this context's mailbox; rank 0 of the group (peerWait off) starts from zero
         unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
-        R.kDev = loc;
         if (s->peerWait)
         {
             LaunchScope ls(c, "pcss_peer_wait", 0);
@@ -1532,26 +1537,36 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
             LaunchScope    ls(c, "pcss_chain", 0);
             FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_chain_fused<kChainNW>, dim3(grid), dim3(1024), args, smemBytes, st));
         }
+    }
+    if (s->peerOn)
+    {   // the band below can start as soon as this band's chain has finished: signal it before anything else is queued
+        unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
+        LaunchScope         ls(c, "pcss_peer_notify", 0);
+        k_peer_notify<<<1, 1, 0, st>>>(s->nextMailbox, s->peerEpoch, loc, (const unsigned*)s->mState.p, blockersBefore, (unsigned)nC1, nU > 0 ? 1 : 0, loc + 1);
+    }
+    }  // !inflight
+    if (phase == FGL_VIS_LAUNCH)
+    {
+        s->chainInFlight = true, s->inflightBefore = blockersBefore;
+        s->prepValid = true, s->prepTotal = nTotal, s->prepLo = siteLo, s->prepHi = siteHi, s->prepNU = nU, s->prepNC1 = nC1;
+        return FGL_OK;
+    }
+    if (nU > 0)
+    {
         unsigned hs[8];
         FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 32, cudaMemcpyDeviceToHost, st));
         FGL_CUDA(c, cudaStreamSynchronize(st));
         c->lastChainIters = (int)hs[CH_ITERS];
         uncertainBlockers = hs[CH_M0];
         if (hs[CH_ERROR] || !hs[CH_DONE]) return fgl_fail(c, FGL_ERR_STATE, "PCSS chain: persistent kernel failed (code " + std::to_string(hs[CH_ERROR]) + ")");
-        if (R.stats)
+        if (s->chainStats.p && getenv("FGL_CHAIN_STATS"))
         {
             unsigned long long hq[16];
-            FGL_CUDA(c, cudaMemcpyAsync(hq, R.stats, 128, cudaMemcpyDeviceToHost, st));
+            FGL_CUDA(c, cudaMemcpyAsync(hq, s->chainStats.p, 128, cudaMemcpyDeviceToHost, st));
             FGL_CUDA(c, cudaStreamSynchronize(st));
             fprintf(stderr, "[chain stats] sites=%zu uncertain=%d iters=%d | pilot pairs=%llu one=%llu ambiguous=%llu taps_in_E=%llu\n", n, nU, c->lastChainIters,
                     hq[0], hq[1], hq[2], hq[3]);
         }
-    }
-    if (s->peerOn)
-    {
-        unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
-        LaunchScope         ls(c, "pcss_peer_notify", 0);
-        k_peer_notify<<<1, 1, 0, st>>>(s->nextMailbox, s->peerEpoch, loc, (const unsigned*)s->mState.p, blockersBefore, (unsigned)nC1, nU > 0 ? 1 : 0, loc + 1);
     }
     {
         LaunchScope ls(c, "pcss_flags", n * 16);
@@ -1596,7 +1611,7 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase)
     bool   pcss = L.shadowMode == FGL_SHADOW_PCSS;
     size_t lo = (size_t)L.row0 * L.W, hi = (size_t)L.row1 * L.W;
     (void)pcss;
-    if (!(phase == FGL_VIS_RESOLVE && s->prepValid))
+    if (!((phase == FGL_VIS_RESOLVE || phase == FGL_VIS_LAUNCH) && s->prepValid))
     {
         LaunchScope ls(c, "shadow_coords", (hi - lo) * (36 + 16));
         k_shadow_coords<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(P, lo, hi, (float4*)s->sc4.p);
@@ -1622,6 +1637,8 @@ int fgl_stream_chain_total(fgl_ctx* c, unsigned long long* out)
     }
     return FGL_OK;
 }
+
+bool fgl_stream_peer_on(fgl_ctx* c) { return c->stream_state && c->stream_state->peerOn; }
 
 // ---- peer hand-off set-up ---------------------------------------------------------------------------------------------
 static int peer_buffers(fgl_ctx* c, SampleStream* s)

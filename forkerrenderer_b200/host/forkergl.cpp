@@ -215,14 +215,14 @@ void ForkerGL::DrawScreenSpacePixels(const Scene& scene)
 }
 
 // sort-first drivers: the band-independent first half of DrawScreenSpacePixels (include/forkergl_b200.h)
-void ForkerGL::PrepareScreenSpacePixels(const Scene& scene)
+void ForkerGL::PrepareScreenSpacePixels(const Scene& scene, bool ssaoFollows)
 {
     Point3f eye = scene.GetCamera().GetPosition();
     Point3f lp = scene.GetPointLight().position;
     Color3  lc = scene.GetPointLight().color;
     float   e[3] = { eye.x, eye.y, eye.z }, p[3] = { lp.x, lp.y, lp.z }, c[3] = { lc.x, lc.y, lc.z };
     InvalidateHostMirrors();
-    Check(fgl_prepare_screen_space_pixels(Context(), e, p, c), "PrepareScreenSpacePixels");
+    Check(fgl_prepare_screen_space_pixels(Context(), e, p, c, ssaoFollows ? 1 : 0), "PrepareScreenSpacePixels");
 }
 
 void ForkerGL::FetchAntiAliasedImage()

@@ -59,7 +59,7 @@ struct ForkerGL
     // Rasterization.  DrawMesh is what Mesh::Draw calls (one indexed draw per mesh).
     static void DrawMesh(const Mesh& mesh, Shader& shader);
     static void DrawScreenSpacePixels(const Scene& scene);
-    static void PrepareScreenSpacePixels(const Scene& scene);  // optional, multi-GPU: see fgl_prepare_screen_space_pixels
+    static void PrepareScreenSpacePixels(const Scene& scene, bool ssaoFollows);  // optional, multi-GPU: see fgl_prepare_screen_space_pixels
 
     // --- additions over the reference surface (device plumbing) ---
     static fgl_ctx* Context();            // lazily created on device $FGL_DEVICE (default 0); aborts loudly on failure

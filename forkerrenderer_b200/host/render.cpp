@@ -56,8 +56,10 @@ void RenderGeometryStage(const Scene& scene)
         ForkerGL::InitFrameBuffer(BufferWidth(scene), BufferHeight(scene));
         ForkerGL::SetPassType(ForkerGL::LightingPass);
         ForkerGL::ClearColor(Color3(0.12f, 0.12f, 0.12f));  // overwritten by the lighting loop, as in the reference
+        // nothing but a head start for the lighting loop: a PCSS frame's sample-stream chain starts here, on its own stream,
+        // and runs while SSAO and the blur do (include/forkergl_b200.h, fgl_prepare_screen_space_pixels)
+        ForkerGL::PrepareScreenSpacePixels(scene, scene.IsSSAOOn());
         if (scene.IsSSAOOn()) DoSSAO(scene);
-        ForkerGL::PrepareScreenSpacePixels(scene);  // nothing but a head start for the lighting loop (multi-GPU hand-off)
     }
 }
 

@@ -180,11 +180,12 @@ class SyntheticScene:
             f.init_frame_buffer(BW, BH)
             f.set_pass_type(B.PASS_LIGHTING)
             f.clear_color((0.12, 0.12, 0.12))
+            # a head start for the lighting pass: everything that does not need the previous band's chain state, and — when
+            # that state is known or arrives on the device — the PCSS chain itself, overlapped with SSAO and the blur
+            f.prepare_screen_space_pixels(self.eye, self.light_pos, self.light_color, ssao)
             if ssao:
                 f.ssao()
                 f.blur(B.PLANE_AO, B.BLUR_TWO_PASS_GAUSSIAN)
-            if band:  # sort-first: everything of the lighting pass that does not need the previous band's chain state
-                f.prepare_screen_space_pixels(self.eye, self.light_pos, self.light_color)
 
     def render_finish(self):
         f = self.f

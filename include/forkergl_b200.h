@@ -203,11 +203,16 @@ int fgl_draw_mesh(fgl_ctx* ctx, int mesh_id, int shader_kind, const FglUniforms*
 /* ForkerGL::DrawScreenSpacePixels (src/forkergl.cpp:326-380), the deferred lighting loop. */
 int fgl_draw_screen_space_pixels(fgl_ctx* ctx, const float eye_position[3], const float light_position[3],
                                  const float light_color[3]);
-/* Optional: the part of the lighting pass that does not depend on the row bands above this context's band (PCSS
- * frames: shadow coordinates, classification, cell masks, pilot).  A sort-first multi-GPU driver calls it before it
- * waits for the previous band's fgl_get_chain_blockers; fgl_draw_screen_space_pixels then only resolves the chain. */
+/* Optional head start for the lighting pass, callable once the geometry pass has been submitted (before fgl_ssao).
+ * PCSS frames: everything that does not depend on the row bands above this context's band (shadow coordinates,
+ * classification, cell masks, pilot), and — when the chain's input is known (a whole-frame context) or arrives on
+ * the device (fgl_chain_peer_connect) — the sample-stream chain kernel itself, issued on a stream of its own so that
+ * SSAO and the blur overlap it.  fgl_draw_screen_space_pixels picks the result up; without this call it does all of
+ * it itself.  A sort-first driver using the HOST hand-off calls it before waiting for fgl_get_chain_blockers of the
+ * band above.  ssao_follows: non-zero iff fgl_ssao will run between this call and fgl_draw_screen_space_pixels (SSAO
+ * consumes the reference's sample stream before the lighting loop does, render.cpp:204-209). */
 int fgl_prepare_screen_space_pixels(fgl_ctx* ctx, const float eye_position[3], const float light_position[3],
-                                    const float light_color[3]);
+                                    const float light_color[3], int ssao_follows);
 
 /* Render::DoSSAO without its trailing blur (src/render.cpp:214-286) */
 int fgl_ssao(fgl_ctx* ctx);
