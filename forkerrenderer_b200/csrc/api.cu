@@ -691,7 +691,8 @@ int fgl_prepare_screen_space_pixels(fgl_ctx* c, const float eye[3], const float 
     // band whose input arrives on the device (fgl_chain_peer_connect).  It goes to its own stream, behind an event, so
     // that whatever the caller queues next on the main stream — SSAO, the blur — runs concurrently with it.
     static const bool noOverlap = getenv("FGL_NO_CHAIN_OVERLAP") != nullptr;
-    if (noOverlap || !(fullBand || fgl_stream_peer_on(c))) return FGL_OK;
+    // (per-kernel event timing is only meaningful without concurrency: the instrumented frames of bench.py run serially)
+    if (noOverlap || (c->timing && !fgl_stream_peer_on(c)) || !(fullBand || fgl_stream_peer_on(c))) return FGL_OK;
     if (!c->chainStream)
     {
         FGL_CUDA(c, cudaStreamCreateWithFlags(&c->chainStream, cudaStreamNonBlocking));
