@@ -39,20 +39,6 @@ __device__ __forceinline__ V3 shade_pixel(const LightPass& L, const PixelIn& in,
     return pbr_light(lc, lightDir, viewDir, vnormalize(vadd(lightDir, viewDir)), in.nrm, visibility, in.albedo, in.emissive, in.param, rad);
 }
 
-__device__ __forceinline__ PixelIn load_pixel(const LightPass& L, size_t n, size_t idx)
-{
-    PixelIn in;
-    in.pos = ld3s(L.planes.p[FGL_PLANE_WORLDPOS], n, idx);
-    in.nrm = ld3s(L.planes.p[FGL_PLANE_NORMAL], n, idx);
-    in.lndc = L.shadowOn ? ld3s(L.planes.p[FGL_PLANE_LIGHTNDC], n, idx) : v3(0.f, 0.f, 0.f);
-    in.albedo = ld3s(L.planes.p[FGL_PLANE_ALBEDO], n, idx);
-    in.emissive = ld3s(L.planes.p[FGL_PLANE_EMISSIVE], n, idx);
-    in.param = ld3s(L.planes.p[FGL_PLANE_PARAM], n, idx);
-    in.type = L.planes.p[FGL_PLANE_SHADINGTYPE][idx];
-    in.param.x *= L.planes.p[FGL_PLANE_AO][idx];  // forkergl.cpp:350
-    return in;
-}
-
 template <int VEC>
 __global__ void __launch_bounds__(128) k_lighting_hard(LightPass L)
 {

@@ -15,10 +15,11 @@
 //
 // PCSS: pixel p (scan order) uses 32 samples and 64 more iff its blocker search found a blocker, so its offset is
 // 32 p + 64 k(p), k(p) = number of earlier pixels with a blocker.  Pixels are first classified with a min/max filter
-// of the shadow map over the search footprint (certainly no blocker / certainly a blocker / uncertain); uncertain
-// pixels are then resolved in scan order in super-chunks of kT pixels: for the t-th pixel of a super-chunk every
-// candidate offset (t + 1 of them) is evaluated in parallel, after which a single thread walks the pixels whose
-// answer actually depends on the offset.
+// of the shadow map over the search footprint (certainly no blocker / certainly a blocker / uncertain); the uncertain
+// pixels are then resolved in scan order, in super-chunks from an exactly known state, by ONE persistent cooperative
+// kernel (k_chain_fused): candidate offsets around a pilot prediction are evaluated in parallel, 32-row segments are
+// turned into transfer tables, and CTA 0 composes the tables in order.  The chain state crosses GPUs through
+// peer-memory mailboxes (k_peer_wait / k_peer_notify).
 #include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
@@ -357,15 +358,6 @@ __global__ void __launch_bounds__(256) k_gather_uncertain(size_t n, const int* i
     Upix[j] = (unsigned)idx, Uc1[j] = (unsigned)c1pre[idx], Usc[j] = sc4[idx];
 }
 
-// blocker flag of one pixel for one candidate chunk: any of the 32 taps blocks (shadow.cpp:65-90)
-__device__ __forceinline__ bool blocker_any(const ShadowMapD& sm, const float2* disk, double fs, float4 s, size_t chunk, int lane)
-{
-    float2 d = __ldg(disk + chunk * 32 + lane);
-    float  ox = (float)((double)d.x * fs), oy = (float)((double)d.y * fs);
-    float  sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
-    return __any_sync(0xffffffffu, s.z > sampleDepth + s.w);
-}
-
 // Per uncertain pixel: F = cells whose every tap certainly blocks, E = cells in which a tap can block at all.
 // A chunk with a sample in an F cell has a blocker; a chunk with no sample in any E cell has none; only the rest
 // needs its 32 taps evaluated.  Cell (kx, ky) covers sample coordinates [-1 + kx/4, -1 + (kx+1)/4]: the tap
@@ -638,7 +630,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* 
         // rr = 32 i + warp is super-chunk row t = (32 i + warp) * G + b.  Tables are per SEGMENT: CTA b builds the tables
         // of segments b, b + G, ... from the rows' bits in global memory after a grid-wide barrier.
         const int mySegs = blockIdx.x < nSeg ? (nSeg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        constexpr int myRows = kRowsCta, myWords = kRowsCta * NW;
+        constexpr int myWords = kRowsCta * NW;
 
         // (1a) warp per row (up to kMaxSpc rows per warp, their loads in flight together): signature test of the W candidates
         {
@@ -1608,9 +1600,7 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase)
     P.worldpos = L.planes.p[FGL_PLANE_WORLDPOS], P.normal = L.planes.p[FGL_PLANE_NORMAL], P.lndc = L.planes.p[FGL_PLANE_LIGHTNDC];
     memcpy(P.lightPos, L.lightPos, 12);
     P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
-    bool   pcss = L.shadowMode == FGL_SHADOW_PCSS;
     size_t lo = (size_t)L.row0 * L.W, hi = (size_t)L.row1 * L.W;
-    (void)pcss;
     if (!((phase == FGL_VIS_RESOLVE || phase == FGL_VIS_LAUNCH) && s->prepValid))
     {
         LaunchScope ls(c, "shadow_coords", (hi - lo) * (36 + 16));

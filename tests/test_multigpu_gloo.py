@@ -72,6 +72,72 @@ def worker(rank, world, port, image, per_row, out):
     dist.destroy_process_group()
 
 
+class NoPeerFgl(FakeFgl):
+    """A context whose library has no peer memory (the CPU oracle answers FGL_ERR_UNSUPPORTED the same way)."""
+
+    def chain_peer_mailbox(self):
+        raise B.FglError("no peer memory here")
+
+    def chain_peer_connect(self, **kw):
+        self.log.append(("peer_connect", kw))
+
+
+class PeerFgl(FakeFgl):
+    """Stand-in for a context with device-side hand-off: records what the driver asked for."""
+
+    def chain_peer_mailbox(self):
+        return 0x1000, bytes([7]) * 64
+
+    def chain_peer_connect(self, **kw):
+        self.log.append(("peer_connect", kw))
+
+
+def peer_worker(rank, world, port, image, per_row, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H = image.shape[0]
+    # every rank must agree: one rank without IPC sends the whole group back to the host hand-off
+    mixed = M.setup_peer_handoff(NoPeerFgl(image, per_row) if rank == 1 else PeerFgl(image, per_row), dist, rank, world, H)
+    fgl = PeerFgl(image, per_row)
+    ok = M.setup_peer_handoff(fgl, dist, rank, world, H)
+    connect = [kw for name, kw in fgl.log if name == "peer_connect"]
+    wired = (len(connect) == 1 and connect[0]["wait_prev"] == (rank > 0)
+             and (connect[0]["next_ipc"] is None) == (rank == world - 1))
+    # with the device-side hand-off the driver neither receives nor sends the chain state
+    r = FakeRenderer(fgl, pcss=False)
+    r.pcss = True
+    r.finish = lambda: None
+
+    class NoComm:
+        def send_int(self, *a):
+            raise AssertionError("host hand-off used although peer=True")
+        recv_int = send_int
+    M.render_frame(r, rank, world, NoComm(), peer=True)
+    # a frame too short for the group (an empty last band) keeps the host hand-off
+    empty = M.setup_peer_handoff(PeerFgl(image, per_row), dist, rank, world, world - 2)
+    out.put((rank, (not mixed) and ok and wired and not empty))
+    dist.destroy_process_group()
+
+
+def test_peer_handoff_setup_and_fallback(oracle_fgl):
+    image = np.zeros((12, 8, 3), dtype=np.uint8)
+    per_row = np.ones(12, dtype=np.int64)
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=peer_worker, args=(r, world, port, image, per_row, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+    # the CPU oracle has no peer memory: the ABI says so instead of pretending
+    with pytest.raises(B.FglError):
+        oracle_fgl.chain_peer_mailbox()
+
+
 def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
