@@ -1,0 +1,36 @@
+"""bench.py's contract that can be checked without a GPU: the reference arm (the unmodified reference on the host cores)
+prints one JSON line with the keys the driver reads, and the product arm refuses loudly when there is no CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import parity as P
+
+BENCH = os.path.join(P.REPO, "bench.py")
+
+
+def test_reference_arm_prints_one_json_line():
+    if not P.have_ref():
+        pytest.skip("oracle/_ref/ref_driver not built")
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mpixels_per_s" and d["unit"] == "Mpixels/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "sample" in d["config"]
+
+
+def test_product_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, BENCH, "--workload", "c1", "--steps", "1", "--no-cpu-baseline"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode != 0 and not r.stdout.strip(), "the product arm must not produce a number without the CUDA path"
