@@ -204,8 +204,12 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; rank 0's stdout is the one JSON line
+        # NCCL writes its debug output — at NCCL_DEBUG=VERSION / WARN that includes a version banner — to STDOUT unless told
+        # otherwise; rank 0's stdout is the one JSON line
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     os.environ["FGL_DEVICE"] = str(local)
