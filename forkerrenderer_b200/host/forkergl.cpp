@@ -16,17 +16,9 @@
 Texture::WrapMode   ForkerGL::TextureWrapping = Texture::NoWrap;
 Texture::FilterMode ForkerGL::TextureFiltering = Texture::Nearest;
 
-Buffer3f ForkerGL::FrameBuffer;
-Buffer1f ForkerGL::DepthBuffer;
-Buffer1f ForkerGL::ShadowBuffer;
-Buffer3f ForkerGL::NormalGBuffer;
-Buffer3f ForkerGL::WorldPosGBuffer;
-Buffer3f ForkerGL::LightSpaceNDCPosGBuffer;
-Buffer3f ForkerGL::AlbedoGBuffer;
-Buffer3f ForkerGL::EmissiveGBuffer;
-Buffer3f ForkerGL::ParamGBuffer;
-Buffer1f ForkerGL::ShadingTypeGBuffer;
-Buffer1f ForkerGL::AmbientOcclusionGBuffer;
+#define FGL_FACADE_DEFINE(TYPE, NAME, PLANE) TYPE ForkerGL::NAME;
+FGL_FACADE_BUFFERS(FGL_FACADE_DEFINE)
+#undef FGL_FACADE_DEFINE
 TGAImage ForkerGL::AntiAliasedImage;
 
 static fgl_ctx*             s_Ctx = nullptr;
@@ -75,9 +67,9 @@ void ForkerGL::Check(int status, const char* what)
 
 void ForkerGL::InvalidateHostMirrors()
 {
-    Buffer* all[] = { &FrameBuffer, &DepthBuffer, &ShadowBuffer, &NormalGBuffer, &WorldPosGBuffer,
-                      &LightSpaceNDCPosGBuffer, &AlbedoGBuffer, &EmissiveGBuffer, &ParamGBuffer,
-                      &ShadingTypeGBuffer, &AmbientOcclusionGBuffer };
+#define FGL_FACADE_ADDRESS(TYPE, NAME, PLANE) &NAME,
+    Buffer* all[] = { FGL_FACADE_BUFFERS(FGL_FACADE_ADDRESS) };
+#undef FGL_FACADE_ADDRESS
     for (Buffer* b : all)
     {
         b->push();  // host edits made through SetValue reach the device before it runs

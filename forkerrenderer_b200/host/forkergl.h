@@ -26,19 +26,24 @@ struct ForkerGL
     static void TextureWrapMode(Texture::WrapMode wrapMode);
     static void TextureFilterMode(Texture::FilterMode filterMode);
 
-    // Buffers (handles onto device planes; see buffer.h)
-    static Buffer3f FrameBuffer;
-    static Buffer1f DepthBuffer;
-    static Buffer1f ShadowBuffer;
-    static Buffer3f NormalGBuffer;
-    static Buffer3f WorldPosGBuffer;
-    static Buffer3f LightSpaceNDCPosGBuffer;
-    static Buffer3f AlbedoGBuffer;
-    static Buffer3f EmissiveGBuffer;
-    static Buffer3f ParamGBuffer;
-    static Buffer1f ShadingTypeGBuffer;
-    static Buffer1f AmbientOcclusionGBuffer;
-    static TGAImage AntiAliasedImage;
+    // The static buffers of the reference (forkergl.h:34-47), here handles onto device planes (buffer.h).  One list feeds the
+    // declarations, the definitions and the host-mirror bookkeeping in forkergl.cpp:  X(type, name, C-ABI plane).
+#define FGL_FACADE_BUFFERS(X)                                      \
+    X(Buffer3f, FrameBuffer, FGL_PLANE_FRAME)                      \
+    X(Buffer1f, DepthBuffer, FGL_PLANE_DEPTH)                      \
+    X(Buffer1f, ShadowBuffer, FGL_PLANE_SHADOW)                    \
+    X(Buffer3f, NormalGBuffer, FGL_PLANE_NORMAL)                   \
+    X(Buffer3f, WorldPosGBuffer, FGL_PLANE_WORLDPOS)               \
+    X(Buffer3f, LightSpaceNDCPosGBuffer, FGL_PLANE_LIGHTNDC)       \
+    X(Buffer3f, AlbedoGBuffer, FGL_PLANE_ALBEDO)                   \
+    X(Buffer3f, EmissiveGBuffer, FGL_PLANE_EMISSIVE)               \
+    X(Buffer3f, ParamGBuffer, FGL_PLANE_PARAM)                     \
+    X(Buffer1f, ShadingTypeGBuffer, FGL_PLANE_SHADINGTYPE)         \
+    X(Buffer1f, AmbientOcclusionGBuffer, FGL_PLANE_AO)
+#define FGL_FACADE_DECLARE(TYPE, NAME, PLANE) static TYPE NAME;
+    FGL_FACADE_BUFFERS(FGL_FACADE_DECLARE)
+#undef FGL_FACADE_DECLARE
+    static TGAImage AntiAliasedImage;  // the SSAA result (render.cpp:291-343), fetched from the device on demand
 
     static void InitFrameBuffer(int width, int height);
     static void InitDepthBuffer(int width, int height);

@@ -23,12 +23,8 @@ void OutputSSAAImage()
     if (ForkerGL::AntiAliasedImage.GetWidth() != 0)
         ForkerGL::AntiAliasedImage.WriteTgaFile(s_Dir + "/framebuffer_SSAA.tga");
 }
-#define FGL_OUT3(FN, BUF, FILE) \
-    void FN() { if (ForkerGL::BUF.GetWidth() != 0) ForkerGL::BUF.GenerateImage().WriteTgaFile(s_Dir + FILE); }
-FGL_OUT3(OutputNormalGBuffer, NormalGBuffer, "/gbuffer_normal.tga")
-FGL_OUT3(OutputWorldPosGBuffer, WorldPosGBuffer, "/gbuffer_worldpos.tga")
-FGL_OUT3(OutputAlbedoGBuffer, AlbedoGBuffer, "/gbuffer_albedo.tga")
-FGL_OUT3(OutputParamGBuffer, ParamGBuffer, "/gbuffer_param.tga")
-FGL_OUT3(OutputShadingTypeGBuffer, ShadingTypeGBuffer, "/gbuffer_shading_type.tga")
-FGL_OUT3(OutputAmbientOcclusionGBuffer, AmbientOcclusionGBuffer, "/gbuffer_ambient_occlusion.tga")
+#define FGL_OUTPUT_DEFINE(NAME, BUFFER, FILE) \
+    void Output##NAME() { if (ForkerGL::BUFFER.GetWidth() != 0) ForkerGL::BUFFER.GenerateImage().WriteTgaFile(s_Dir + FILE); }
+FGL_OUTPUT_GBUFFER_DUMPS(FGL_OUTPUT_DEFINE)
+#undef FGL_OUTPUT_DEFINE
 }  // namespace Output
