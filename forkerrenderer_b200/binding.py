@@ -365,11 +365,15 @@ class Host:
         self._ck(self.lib.frh_set_camera(scene.handle, (C.c_float * 3)(*eye), (C.c_float * 3)(*look_at)),
                  "frh_set_camera")
 
+    def set_point_light(self, scene, position, color):
+        self.lib.frh_set_point_light.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._ck(self.lib.frh_set_point_light(scene.handle, (C.c_float * 3)(*position), (C.c_float * 3)(*color)), "frh_set_point_light")
+
     def output_tga(self, directory):
         self._ck(self.lib.frh_output_tga(os.fsencode(directory)), "frh_output_tga")
 
     def test_matrices(self, t, rot, scale, eye, center, ratio):
-        out = (C.c_float * 89)()
+        out = (C.c_float * 105)()
         self.lib.frh_test_matrices.restype = None
         self.lib.frh_test_matrices((C.c_float * 3)(*t), C.c_float(rot), C.c_float(scale), (C.c_float * 3)(*eye),
                                    (C.c_float * 3)(*center), C.c_float(ratio), out)

@@ -102,6 +102,15 @@ int frh_set_camera(void* scene, const float eye[3], const float look_at[3])
     });
 }
 
+int frh_set_point_light(void* scene, const float position[3], const float color[3])
+{
+    return Guard([&] {
+        PointLight& l = ((Scene*)scene)->GetPointLight();
+        l.position = Vector3f(position[0], position[1], position[2]);
+        l.color = Vector3f(color[0], color[1], color[2]);
+    });
+}
+
 // One frame: Render::Preconfigure + Render::Render (reference main.cpp:37-40).
 int frh_render(void* scene, int shadow_mode, int materialize_frame_f32)
 {
@@ -152,7 +161,7 @@ int frh_output_tga(const char* dir)
 }
 
 // Host matrix builders, for the bit-exactness test against the reference's (tests/test_host_math.py).
-// out = model(16) normal(9) lookat(16) persp(16) ortho(16) ortho*lookat(16)
+// out = model(16) normal(9) lookat(16) persp(16) ortho(16) ortho*lookat(16) persp*lookat(16) = 105 floats
 void frh_test_matrices(const float t[3], float rot, float scale, const float eye[3], const float center[3],
                        float ratio, float* out)
 {
@@ -161,11 +170,11 @@ void frh_test_matrices(const float t[3], float rot, float scale, const float eye
     Matrix4x4f L = MakeLookAtMatrix(Vector3f(eye[0], eye[1], eye[2]), Vector3f(center[0], center[1], center[2]));
     Matrix4x4f P = MakePerspectiveMatrix(45.f, ratio, 0.01f, 20.f);
     Matrix4x4f O = MakeOrthographicMatrix(-3 * ratio, 3 * ratio, -3, 3, 0.1f, 20.f);
-    Matrix4x4f OL = O * L;
+    Matrix4x4f OL = O * L, PL = P * L;
     int        k = 0;
     auto put4 = [&](const Matrix4x4f& m) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[k++] = m[r][c]; };
     put4(M);
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) out[k++] = N[r][c];
-    put4(L), put4(P), put4(O), put4(OL);
+    put4(L), put4(P), put4(O), put4(OL), put4(PL);
 }
 }  // extern "C"

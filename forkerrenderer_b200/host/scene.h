@@ -24,6 +24,7 @@ public:
     bool IsSSAOOn() const { return m_SSAO; }
 
     const PointLight& GetPointLight() const { assert(m_PointLight); return *m_PointLight; }
+    PointLight&       GetPointLight() { assert(m_PointLight); return *m_PointLight; }  // multi-frame use (animated light)
     const DirLight&   GetDirLight() const { assert(m_DirLight); return *m_DirLight; }
     const Camera&     GetCamera() const { assert(m_Camera); return *m_Camera; }
     Camera&           GetCamera() { assert(m_Camera); return *m_Camera; }

@@ -7,6 +7,7 @@
 //
 // Usage: ref_driver --assets DIR --scene FILE --out DIR [--shadow hard|pcf|pcss] [--wrap 0..3]
 //                   [--filter 0|1] [--ids] [--tga] [--frames N] [--quiet]
+//        ref_driver --buffer-test OUTDIR | --matrices <12 floats>
 //   --assets   directory that contains obj/ (the reference opens model paths relative to the CWD)
 //   --wrap/--filter are applied BEFORE the Scene is constructed, because textures capture the modes at
 //   load time (reference model.cpp:425).
@@ -15,6 +16,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "output.h"
@@ -189,9 +191,37 @@ static int BufferTest(const std::string& out)
     return 0;
 }
 
+// --matrices tx ty tz rotY scale ex ey ez cx cy cz ratio: the reference's host uniform builders (geometry.cpp:60-68,92-179,
+// geometry.h:784-793) on one parameter set; prints the 105 floats as hex words in the order of the facade's
+// frh_test_matrices: model(16) normal(9) lookat(16) persp(16) ortho(16) ortho*lookat(16) persp*lookat(16).
+static int MatrixTest(int argc, const char* argv[])
+{
+    if (argc != 14) return 2;
+    float a[12];
+    for (int i = 0; i < 12; ++i) a[i] = strtof(argv[2 + i], nullptr);
+    Matrix4x4f M = MakeModelMatrix(Vector3f(a[0], a[1], a[2]), a[3], a[4]);
+    Matrix3x3f N = MakeNormalMatrix(M);
+    Matrix4x4f L = MakeLookAtMatrix(Vector3f(a[5], a[6], a[7]), Vector3f(a[8], a[9], a[10]));
+    Matrix4x4f P = MakePerspectiveMatrix(45.f, a[11], 0.01f, 20.f);
+    Matrix4x4f O = MakeOrthographicMatrix(-3 * a[11], 3 * a[11], -3, 3, 0.1f, 20.f);
+    Matrix4x4f OL = O * L, PL = P * L;
+    auto put = [](float f) {
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        printf("%08x ", u);
+    };
+    auto put4 = [&](const Matrix4x4f& m) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) put(m[r][c]); };
+    put4(M);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) put(N[r][c]);
+    put4(L), put4(P), put4(O), put4(OL), put4(PL);
+    printf("\n");
+    return 0;
+}
+
 int main(int argc, const char* argv[])
 {
     if (argc == 3 && std::string(argv[1]) == "--buffer-test") return BufferTest(argv[2]);
+    if (argc >= 2 && std::string(argv[1]) == "--matrices") return MatrixTest(argc, argv);
     std::string assets = ".", sceneFile, out = ".", shadow = "pcss";
     int         wrap = 0, filter = 0, frames = 1;
     bool        ids = false, tga = false, quiet = false;

@@ -29,7 +29,16 @@ def fingerprint(a):
 def main():
     out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_hashes.json")
     golden = json.load(open(out_path)) if os.path.exists(out_path) else {}
-    cfgs = sys.argv[1:] or (list(P.CONFIGS) + ["buffer_ops"])
+    cfgs = sys.argv[1:] or (list(P.CONFIGS) + ["buffer_ops", "host_math", "tga_files"])
+    if "host_math" in cfgs:  # the reference's host uniform builders (geometry.cpp:60-68,92-179), words as hex
+        cfgs.remove("host_math")
+        golden["host_math"] = [{"case": [float(np.float32(v)) for v in case], "words": ["%08x" % w for w in P.run_reference_matrices(case)]}
+                               for case in P.MATRIX_CASES]
+        print("host_math ok", flush=True)
+    if "tga_files" in cfgs:  # md5 of the files the reference's Output::* writes (tgaimage.cpp:43-246, output.cpp:12-86)
+        cfgs.remove("tga_files")
+        golden["tga_files"] = {cfg: P.run_reference_tga(cfg) for cfg in ("c4_hard", "c2_hard")}
+        print("tga_files ok", flush=True)
     if "buffer_ops" in cfgs:  # Buffer1f / Buffer3f SimpleBlurDenoised and TwoPassGaussianBlurDenoised (buffer.cpp:35-98, 140-203)
         cfgs.remove("buffer_ops")
         golden["buffer_ops"] = {k: {"buffer1f": fingerprint(v[0]), "buffer3f": fingerprint(v[1])} for k, v in sorted(P.run_reference_buffer_ops().items())}

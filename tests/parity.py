@@ -30,7 +30,59 @@ CONFIGS = {
     "c4_hard": ("scenes/c4.scene", "hard", 0, 0),
     "c4_catbox_linear": ("scenes/c4_catbox.scene", "hard", 1, 1),
     "pbr_hard": ("scenes/pbr.scene", "hard", 0, 0),
+    # round 2: forward-mode PBR program, PBR + PCSS + SSAO, the remaining wrap modes, a second camera / light, the orthographic camera
+    "fwd_pbr_hard": ("scenes/fwd_pbr.scene", "hard", 0, 0),
+    "fwd_pbr_pcf": ("scenes/fwd_pbr.scene", "pcf", 0, 0),
+    "fwd_pbr_pcss": ("scenes/fwd_pbr.scene", "pcss", 0, 0),
+    "pbr_ssao_pcss": ("scenes/pbr_ssao.scene", "pcss", 0, 0),
+    "c3_pbr_pcss_ssao": ("scenes/c3_pbr.scene", "pcss", 0, 0),
+    "catbox_mirrored_linear": ("scenes/catbox.scene", "hard", 2, 1),
+    "catbox_mirrored_nearest": ("scenes/catbox.scene", "hard", 2, 0),
+    "catbox_clamp_linear": ("scenes/catbox.scene", "hard", 3, 1),
+    "catbox_clamp_nearest": ("scenes/catbox.scene", "hard", 3, 0),
+    "catbox_repeat_nearest": ("scenes/catbox.scene", "hard", 1, 0),
+    "catbox_nowrap_linear": ("scenes/catbox.scene", "hard", 0, 1),
+    "c1_cam2_pcss": ("scenes/c1_cam2.scene", "pcss", 0, 0),
+    "c1_ortho_hard": ("scenes/c1_ortho.scene", "hard", 0, 0),
 }
+
+# parameter sets of the host uniform builders (tests/test_host_math.py): translate xyz, rotY degrees, scale, eye xyz, centre xyz, ratio
+MATRIX_CASES = [
+    (0, -1, -1, 0, 3, -1, 1, 1, 0, 0, -1, 1.6),
+    (0.05, 0, -1, -10, 1, -1, 1, 1, 0, 0, -1, 1.6),
+    (0.9, 0, -1, -90, 1, 2, 5, 5, 0, 0, 0, 1.7777778),
+    (-0.7, 0, -1, 40, 1, 1.2, 0.6, 0.8, 0.1, -0.2, -1, 1.7777778),
+    (0, 0.3, -1, 240, 1, -1.5, 4, 3, 0, 0, 0, 1.0),
+    (-1.2, -0.7, -0.6, 30, 0.3, 0.3, 2.5, -4, 0.5, 0.25, 1, 0.5625),
+    (0, -0.5, -1, 180, 2.5, 7, 0.01, 0.02, -3, 1, 2, 2.3333333),
+    (3.25, -2.5, 1.125, 359.5, 0.015625, -0.001, 12, 0.003, 0, 0, -1, 1.3333334),
+]
+
+
+def run_reference_matrices(case):
+    """105 float32 words of the reference's MakeModelMatrix / MakeNormalMatrix / MakeLookAtMatrix / MakePerspectiveMatrix /
+    MakeOrthographicMatrix and two products (ref_driver --matrices), as uint32."""
+    r = subprocess.run([REF_DRIVER, "--matrices"] + [repr(float(np.float32(v))) for v in case], check=True, stdout=subprocess.PIPE, text=True)
+    return np.array([int(w, 16) for w in r.stdout.split()], dtype=np.uint32)
+
+
+TGA_FILES = ["framebuffer.tga", "framebuffer_SSAA.tga", "shadowmap.tga", "zbuffer.tga", "gbuffer_normal.tga", "gbuffer_worldpos.tga",
+             "gbuffer_albedo.tga", "gbuffer_param.tga", "gbuffer_shading_type.tga", "gbuffer_ambient_occlusion.tga"]
+
+
+def run_reference_tga(cfg):
+    """{file name: md5} of the TGA files the reference's own Output::* writes for a config (ref_driver --tga)."""
+    import hashlib
+    scene, shadow, wrap, filt = CONFIGS[cfg]
+    out_dir = os.path.join(tempfile.gettempdir(), "fgl_ref_tga_" + cfg)
+    os.makedirs(out_dir, exist_ok=True)
+    tga_dir = os.path.join(ASSETS, "output")
+    for f in TGA_FILES:
+        if os.path.exists(os.path.join(tga_dir, f)):
+            os.unlink(os.path.join(tga_dir, f))
+    subprocess.run([REF_DRIVER, "--assets", ASSETS, "--scene", os.path.join(REPO, scene), "--out", out_dir, "--shadow", shadow, "--wrap", str(wrap),
+                    "--filter", str(filt), "--quiet", "--tga"], check=True, stdout=subprocess.DEVNULL)
+    return {f: hashlib.md5(open(os.path.join(tga_dir, f), "rb").read()).hexdigest() for f in TGA_FILES if os.path.exists(os.path.join(tga_dir, f))}
 
 
 BUFFER_SHAPES = [(5, 4), (33, 7), (1, 9), (9, 1), (64, 48)]

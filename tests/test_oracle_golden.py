@@ -10,8 +10,10 @@ import pytest
 import parity as P
 from conftest import sha
 
-FAST = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c2_pcf", "c4_hard", "c4_catbox_linear", "pbr_hard"]
-SLOW = ["c3_pcss_ssao"]
+FAST = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c2_pcf", "c4_hard", "c4_catbox_linear", "pbr_hard",
+        "fwd_pbr_hard", "fwd_pbr_pcf", "fwd_pbr_pcss", "pbr_ssao_pcss", "catbox_mirrored_linear", "catbox_mirrored_nearest", "catbox_clamp_linear",
+        "catbox_clamp_nearest", "catbox_repeat_nearest", "catbox_nowrap_linear", "c1_cam2_pcss", "c1_ortho_hard"]
+SLOW = ["c3_pcss_ssao", "c3_pbr_pcss_ssao"]
 
 
 def check(cfg, oracle_host, golden):
