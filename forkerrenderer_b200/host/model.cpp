@@ -10,6 +10,12 @@
 // Number parsing goes through std::istringstream like the reference so that odd tokens behave identically.
 #include "model.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <charconv>
 #include <cstring>
 #include <fstream>
 #include <limits>
@@ -85,20 +91,130 @@ void Model::normalizePositionVertices()
     for (Vector3f& v : m_Verts) v = (m * Vector4f(v, 1.f)).xyz();
 }
 
+// ---- OBJ reading -----------------------------------------------------------------------------------------------------
+// The reference reads every line through std::istringstream (model.cpp:143-255), which takes minutes on the 10 M-triangle
+// workload.  Here the file is mapped and scanned in place: "v" / "vt" / "vn" / "f" lines in plain form
+// — decimal tokens separated by blanks, "a/b/c" corners — are decoded with std::from_chars, which like the stream
+// extraction of the reference (libstdc++ num_get -> strtof) returns the correctly rounded float, so both produce the
+// same bits.  Any line that is not in that plain form (a sign, hex, "1//3", junk behind a number ...) goes through the
+// same istringstream statements as before, so odd files behave exactly as they did.
+namespace
+{
+inline bool IsBlank(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
+
+// one float token in plain form; advances p behind it
+inline bool FastFloat(const char*& p, const char* end, float& out)
+{
+    while (p < end && IsBlank(*p)) ++p;
+    const char* b = p;
+    while (p < end && !IsBlank(*p)) ++p;
+    if (b == p) return false;
+    for (const char* q = b; q < p; ++q)
+        if (!((*q >= '0' && *q <= '9') || *q == '-' || *q == '.' || *q == 'e' || *q == 'E')) return false;
+    auto r = std::from_chars(b, p, out);
+    if (r.ec != std::errc() || r.ptr != p) return false;
+    float a = out < 0 ? -out : out;
+    return a == 0.f || a >= std::numeric_limits<float>::min();  // subnormals / underflow: let the stream decide
+}
+inline bool FastUnsigned(const char*& p, const char* end, unsigned& out)
+{
+    const char* b = p;
+    unsigned long long v = 0;
+    while (p < end && *p >= '0' && *p <= '9' && p - b < 10) v = v * 10 + (unsigned)(*p++ - '0');
+    if (b == p || v > 0xffffffffull || (p < end && *p >= '0' && *p <= '9')) return false;
+    out = (unsigned)v;
+    return true;
+}
+struct Corner { int v, t, n; };
+// "f a/b/c a/b/c ..." in plain form
+inline bool FastFace(const char* p, const char* end, std::vector<Corner>& corners)
+{
+    corners.clear();
+    for (;;)
+    {
+        while (p < end && IsBlank(*p)) ++p;
+        if (p == end) return true;
+        unsigned v, t, n;
+        if (!FastUnsigned(p, end, v) || p == end || *p++ != '/' || !FastUnsigned(p, end, t) || p == end || *p++ != '/' || !FastUnsigned(p, end, n))
+            return false;
+        if (p < end && !IsBlank(*p)) return false;
+        corners.push_back({ (int)(v - 1), (int)(t - 1), (int)(n - 1) });
+    }
+}
+}  // namespace
+
 bool Model::loadObjectFile(const std::string& filename, bool flipVertically)
 {
-    std::ifstream in(filename);
-    if (in.fail()) return false;
-
-    std::string line, meshName, materialName;
-    while (!in.eof())
+    int fd = open(filename.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode))
     {
-        std::getline(in, line);
-        line = LeftTrim(line);
+        close(fd);
+        return false;
+    }
+    const size_t size = (size_t)sb.st_size;
+    const char*  data = size ? (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0) : "";
+    close(fd);
+    if (size && data == (const char*)MAP_FAILED) return false;
+
+    std::string         line, meshName, materialName;
+    std::vector<Corner> corners;
+    Mesh*               mesh = nullptr;  // m_Meshes[meshName], looked up once per "g" line instead of once per face
+    auto addFace = [&]() {
+        if (!mesh) mesh = m_Meshes[meshName].get();
+        if (!mesh) throw std::runtime_error("OBJ: face before any 'g' line in " + filename + " (the reference dereferences a null mesh here)");
+        for (size_t i = 1; i + 1 < corners.size(); ++i)  // triangle fan around corner 0
+        {
+            const Corner* tri[3] = { &corners[0], &corners[i], &corners[i + 1] };
+            for (const Corner* c : tri)
+            {
+                mesh->AddVertIndex(c->v);
+                mesh->AddTexCoordIndex(c->t);
+                mesh->AddNormalIndex(c->n);
+            }
+        }
+    };
+    const char* const fileEnd = data + size;
+    for (const char* cur = data; cur <= fileEnd;)
+    {
+        const char* nl = (const char*)memchr(cur, '\n', (size_t)(fileEnd - cur));
+        const char* b = cur, *e = nl ? nl : fileEnd;
+        cur = e + 1;  // (a file without a final newline ends the loop after its last line)
+        while (b < e && (IsBlank(*b) || *b == '\n')) ++b;
+        if (b == e) continue;
+        // plain numeric lines, decoded in place
+        if (b[0] == 'v' && e - b > 2)
+        {
+            const char* p = b + 2;
+            if (b[1] == ' ')
+            {
+                Vector3f v;
+                if (FastFloat(p, e, v.x) && FastFloat(p, e, v.y) && FastFloat(p, e, v.z)) { m_Verts.push_back(v); continue; }
+            }
+            else if (b[1] == 'n' && b[2] == ' ')
+            {
+                Vector3f n;
+                ++p;
+                if (FastFloat(p, e, n.x) && FastFloat(p, e, n.y) && FastFloat(p, e, n.z)) { m_Normals.push_back(n); continue; }
+            }
+            else if (b[1] == 't' && b[2] == ' ')
+            {
+                Vector2f t;
+                ++p;
+                if (FastFloat(p, e, t.x) && FastFloat(p, e, t.y)) { m_TexCoords.push_back(t); continue; }
+            }
+        }
+        else if (b[0] == 'f' && e - b > 2 && b[1] == ' ' && FastFace(b + 2, e, corners))
+        {
+            addFace();
+            continue;
+        }
+        // everything else: the statements of the reference's parser on this line
+        line.assign(b, e);
         std::istringstream iss(line.c_str());
         char               ch;
         std::string        word;
-
         if (StartsWith(line, "mtllib "))
         {
             std::string mtl;
@@ -129,6 +245,7 @@ bool Model::loadObjectFile(const std::string& filename, bool flipVertically)
         {
             iss >> ch >> meshName;
             m_Meshes[meshName] = std::make_shared<Mesh>(*this);
+            mesh = m_Meshes[meshName].get();
         }
         else if (StartsWith(line, "usemtl "))
         {
@@ -139,23 +256,13 @@ bool Model::loadObjectFile(const std::string& filename, bool flipVertically)
         else if (StartsWith(line, "f "))
         {
             iss >> ch;
-            struct Corner { int v, t, n; };
-            std::vector<Corner> corners;
-            unsigned int        v, t, n;
+            corners.clear();
+            unsigned int v, t, n;
             while (iss >> v >> ch >> t >> ch >> n) corners.push_back({ (int)(v - 1), (int)(t - 1), (int)(n - 1) });
-            Mesh& mesh = *m_Meshes[meshName];
-            for (size_t i = 1; i + 1 < corners.size(); ++i)  // triangle fan around corner 0
-            {
-                const Corner* tri[3] = { &corners[0], &corners[i], &corners[i + 1] };
-                for (const Corner* c : tri)
-                {
-                    mesh.AddVertIndex(c->v);
-                    mesh.AddTexCoordIndex(c->t);
-                    mesh.AddNormalIndex(c->n);
-                }
-            }
+            addFace();
         }
     }
+    if (size) munmap((void*)data, size);
     return true;
 }
 

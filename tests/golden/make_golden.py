@@ -48,6 +48,8 @@ def main():
         meta = ref.pop("meta")
         entry = {"scene": P.CONFIGS[cfg][0], "shadow": P.CONFIGS[cfg][1], "wrap": P.CONFIGS[cfg][2], "filter": P.CONFIGS[cfg][3],
                  "width": meta["width"], "height": meta["height"], "planes": {k: fingerprint(v) for k, v in sorted(ref.items())}}
+        if P.CONFIGS[cfg][0].startswith("@"):
+            entry["generated_obj_md5"] = P.generated_input_md5(cfg)
         golden[cfg] = entry
         print(cfg, "ok (reference frame %.2f s)" % meta["t_frame"], flush=True)
     json.dump(golden, open(out_path, "w"), indent=1, sort_keys=True)

@@ -44,7 +44,33 @@ CONFIGS = {
     "catbox_nowrap_linear": ("scenes/catbox.scene", "hard", 0, 1),
     "c1_cam2_pcss": ("scenes/c1_cam2.scene", "pcss", 0, 0),
     "c1_ortho_hard": ("scenes/c1_ortho.scene", "hard", 0, 0),
+    # C5 at the size the reference itself rendered: generated OBJ / MTL / TGA / .scene (forkerrenderer_b200/c5.py),
+    # 500 x 500 quads = 500 000 triangles, deferred PBR, PCSS + SSAO, Repeat + Linear textures
+    "c5_golden": ("@c5_golden", "pcss", 1, 1),
 }
+
+
+def resolve_scene(cfg):
+    """(absolute scene path, assets directory) of a config; '@name' scenes are generated on demand (forkerrenderer_b200/c5.py)."""
+    scene = CONFIGS[cfg][0]
+    if scene.startswith("@"):
+        from forkerrenderer_b200 import c5
+        root, path = c5.ensure(*c5.INSTANCES[scene[1:]])
+        return path, root
+    return os.path.join(REPO, scene), ASSETS
+
+
+def generated_input_md5(cfg):
+    """md5 of the generated OBJ of an '@' config (pinned in the golden file: the generator must be deterministic)."""
+    import hashlib
+    from forkerrenderer_b200 import c5
+    path, root = resolve_scene(cfg)
+    quads = c5.INSTANCES[CONFIGS[cfg][0][1:]][0]
+    h = hashlib.md5()
+    with open(os.path.join(root, "obj", "c5_%d" % quads, "field.obj"), "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 22), b""):
+            h.update(chunk)
+    return h.hexdigest()
 
 # parameter sets of the host uniform builders (tests/test_host_math.py): translate xyz, rotY degrees, scale, eye xyz, centre xyz, ratio
 MATRIX_CASES = [
@@ -136,7 +162,8 @@ def run_reference(cfg, out_dir=None, ids=True):
     os.makedirs(out_dir, exist_ok=True)
     meta_path = os.path.join(out_dir, "meta.json")
     if not os.path.exists(meta_path):
-        cmd = [REF_DRIVER, "--assets", ASSETS, "--scene", os.path.join(REPO, scene), "--out", out_dir, "--shadow", shadow,
+        scene_path, assets = resolve_scene(cfg)
+        cmd = [REF_DRIVER, "--assets", assets, "--scene", scene_path, "--out", out_dir, "--shadow", shadow,
                "--wrap", str(wrap), "--filter", str(filt), "--quiet"] + (["--ids"] if ids else [])
         subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     meta = json.load(open(meta_path))
@@ -161,7 +188,8 @@ def run_reference(cfg, out_dir=None, ids=True):
 def render_host(host, cfg, planes=None, materialize=True):
     """Renders a config through a Host facade (product or oracle-linked) and reads the planes back."""
     scene, shadow, wrap, filt = CONFIGS[cfg]
-    sc = host.load_scene(os.path.join(REPO, scene), ASSETS, wrap, filt)
+    scene_path, assets = resolve_scene(cfg)
+    sc = host.load_scene(scene_path, assets, wrap, filt)
     try:
         host.render(sc, shadow, materialize)
         f = host.fgl

@@ -12,7 +12,9 @@ pytestmark = pytest.mark.gpu
 CONFIGS = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c2_pcf", "c4_hard", "c4_catbox_linear", "pbr_hard", "c3_pcss_ssao",
            # round 2: forward PBR program (hard / PCF / PCSS), PBR + PCSS + SSAO (1280x800 and 4K), wrap modes 2 / 3, second camera, ortho
            "fwd_pbr_hard", "fwd_pbr_pcf", "fwd_pbr_pcss", "pbr_ssao_pcss", "c3_pbr_pcss_ssao", "catbox_mirrored_linear", "catbox_mirrored_nearest",
-           "catbox_clamp_linear", "catbox_clamp_nearest", "catbox_repeat_nearest", "catbox_nowrap_linear", "c1_cam2_pcss", "c1_ortho_hard"]
+           "catbox_clamp_linear", "catbox_clamp_nearest", "catbox_repeat_nearest", "catbox_nowrap_linear", "c1_cam2_pcss", "c1_ortho_hard",
+           # C5 (generated OBJ / MTL / TGA / .scene through the facade's loaders; 500 000 triangles: k_raster_small + device-wide scan)
+           "c5_golden"]
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)

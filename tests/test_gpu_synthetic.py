@@ -29,6 +29,13 @@ CASES = {
     "forward_pcf_dense": dict(shadow_mode=B.SHADOW_PCF, forward=True, quads=96, size=(200, 120)),
     "odd_size_pcss": dict(shadow_mode=B.SHADOW_PCSS, ssao=True, size=(333, 211)),
     "dense_mesh": dict(shadow_mode=B.SHADOW_PCSS, quads=160, size=(256, 160)),
+    # the raster path of the high-triangle-count workload (C5): >= 65 536 triangles per pass switches the small triangles to the
+    # thread-per-triangle kernel (k_raster_small), >= 200 000 switches the block-count scan to the device-wide one
+    "mesh_80k_pcss_ssao": dict(shadow_mode=B.SHADOW_PCSS, ssao=True, pbr=True, quads=200, size=(256, 160)),
+    "mesh_80k_forward_pcf": dict(shadow_mode=B.SHADOW_PCF, forward=True, quads=200, size=(200, 120)),
+    "mesh_231k_pcss_ssao": dict(shadow_mode=B.SHADOW_PCSS, ssao=True, pbr=True, quads=340, size=(320, 200)),
+    "mesh_231k_forward_pcf": dict(shadow_mode=B.SHADOW_PCF, forward=True, quads=340, size=(200, 120)),
+    "mesh_231k_hard_ssaa2": dict(shadow_mode=B.SHADOW_HARD, ssaa=2, quads=340, size=(160, 100)),
 }
 
 

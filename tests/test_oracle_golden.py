@@ -12,7 +12,7 @@ from conftest import sha
 
 FAST = ["c1_hard", "c1_pcf", "c1_pcss", "c1_ssao_pcss", "c2_hard", "c2_pcf", "c4_hard", "c4_catbox_linear", "pbr_hard",
         "fwd_pbr_hard", "fwd_pbr_pcf", "fwd_pbr_pcss", "pbr_ssao_pcss", "catbox_mirrored_linear", "catbox_mirrored_nearest", "catbox_clamp_linear",
-        "catbox_clamp_nearest", "catbox_repeat_nearest", "catbox_nowrap_linear", "c1_cam2_pcss", "c1_ortho_hard"]
+        "catbox_clamp_nearest", "catbox_repeat_nearest", "catbox_nowrap_linear", "c1_cam2_pcss", "c1_ortho_hard", "c5_golden"]
 SLOW = ["c3_pcss_ssao", "c3_pbr_pcss_ssao"]
 
 
@@ -51,6 +51,11 @@ def test_golden_was_generated_by_the_reference_when_it_is_here(golden):
     ref = P.run_reference("c1_hard")
     for name in ("depth", "frame_u8", "ids_camera", "normal"):
         assert sha(ref[name]) == golden["c1_hard"]["planes"][name]["sha256"], name
+
+
+def test_generated_c5_input_is_the_one_the_reference_rendered(golden):
+    """The C5 assets are generated, not committed: the generator must reproduce the OBJ the golden was made from."""
+    assert P.generated_input_md5("c5_golden") == golden["c5_golden"]["generated_obj_md5"]
 
 
 @pytest.mark.parametrize("kind", sorted(P.BUFFER_KINDS))
