@@ -287,6 +287,11 @@ class Fgl:
         return [dict(name=arr[i].name.decode(), ms_total=arr[i].ms_total, launches=arr[i].launches,
                      algorithmic_bytes=arr[i].algorithmic_bytes) for i in range(n.value)]
 
+    def transfer_bytes(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.call("fgl_transfer_bytes", C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def launch_count(self):
         v = C.c_uint64(0)
         self.call("fgl_launch_count", C.byref(v))

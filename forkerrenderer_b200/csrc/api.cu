@@ -45,14 +45,25 @@ static void release(DevBuf& b)
     b.p = nullptr, b.cap = 0;
 }
 
-void fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes)
+// Per-launch timing records are bounded (kMaxTimingRecs; later launches are not recorded until fgl_reset_timings) and
+// their events are recycled through c->eventPool, so a long run with timing on does not accumulate CUDA events.
+static constexpr size_t kMaxTimingRecs = 1 << 16;
+static cudaEvent_t take_event(fgl_ctx* c)
 {
+    cudaEvent_t e = nullptr;
+    if (!c->eventPool.empty()) e = c->eventPool.back(), c->eventPool.pop_back();
+    else cudaEventCreate(&e);
+    return e;
+}
+bool fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes, const unsigned* lateCount, uint64_t lateBytesEach)
+{
+    if (c->timings.size() >= kMaxTimingRecs) return false;
     TimingRec r;
-    r.name = name, r.bytes = bytes;
-    cudaEventCreate(&r.e0);
-    cudaEventCreate(&r.e1);
+    r.name = name, r.bytes = bytes, r.lateCount = lateCount, r.lateBytesEach = lateBytesEach;
+    r.e0 = take_event(c), r.e1 = take_event(c);
     cudaEventRecord(r.e0, c->stream);
     c->timings.push_back(r);
+    return true;
 }
 void fgl_time_end(fgl_ctx* c) { cudaEventRecord(c->timings.back().e1, c->stream); }
 
@@ -139,6 +150,7 @@ int upload_tex_table(fgl_ctx* c)
     for (size_t i = 0; i < c->textures.size(); ++i) t[i] = c->textures[i].desc;
     if (int rc = fgl_reserve(c, c->texTable, t.size() * sizeof(TexD))) return rc;
     FGL_CUDA(c, cudaMemcpyAsync(c->texTable.p, t.data(), t.size() * sizeof(TexD), cudaMemcpyHostToDevice, c->stream));
+    c->h2dBytes += t.size() * sizeof(TexD);
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
     c->texTableDirty = false;
     return FGL_OK;
@@ -192,21 +204,28 @@ int flush(fgl_ctx* c)
     int&    vw = shadowPass ? c->visLightW : c->visCamW;
     int&    vh = shadowPass ? c->visLightH : c->visCamH;
     // InitDepthBuffer (forkergl.cpp:60-63) re-creates the depth buffer the NEXT raster pass tests against
-    if (c->depthInitPending) visClear = true, c->depthInitPending = false;
+    if (c->depthInitPending) visClear = true, c->depthInitPending = c->depthInitBound = false;
     if (vw != P.W || vh != P.H) visClear = true;
+    if (c->passRestarted && !visClear)
+    {   // SetPassType restarted the primitive numbering, but the visibility buffer still holds (depth | id) keys of the pass
+        // before it: their ids would be decoded against this pass's triangles.  The reference keeps testing against the old
+        // depths here (no InitDepthBuffer in between); that sequence is not supported — say so instead of drawing garbage.
+        c->flushedPrims = c->primCounter;
+        return fgl_fail(c, FGL_ERR_UNSUPPORTED, "a raster pass was restarted (SetPassType) without InitDepthBuffer: depth carried over between passes is not supported");
+    }
+    c->passRestarted = false;
     if (int rc = fgl_reserve(c, vis, nPix * 8)) return rc;
     vw = P.W, vh = P.H;
     if (visClear)
     {
-        ++c->launches;
-        if (c->timing) fgl_time_begin(c, "vis_clear", nPix * 8);
+        LaunchScope ls(c, "vis_clear", nPix * 8);
         FGL_CUDA(c, cudaMemsetAsync(vis.p, 0xFF, nPix * 8, c->stream));
-        if (c->timing) fgl_time_end(c);
         visClear = false;
     }
     int nPrims = c->primCounter, nNew = nPrims - c->flushedPrims;
     if (int rc = fgl_reserve(c, c->drawsDev, c->draws.size() * sizeof(DrawCmdD))) return rc;
     FGL_CUDA(c, cudaMemcpyAsync(c->drawsDev.p, c->draws.data(), c->draws.size() * sizeof(DrawCmdD), cudaMemcpyHostToDevice, c->stream));
+    c->h2dBytes += c->draws.size() * sizeof(DrawCmdD);
     if (int rc = fgl_reserve(c, c->setup, (size_t)nPrims * sizeof(TriSetup))) return rc;
     if (shadowPass) { if (int rc = fgl_reserve(c, c->zndc, (size_t)nPrims * sizeof(float4))) return rc; }
     else if (int rc = fgl_reserve(c, c->vary, (size_t)nPrims * sizeof(TriVary))) return rc;
@@ -281,7 +300,7 @@ int flush(fgl_ctx* c)
     bool stochasticForward = c->pass == FGL_PASS_FORWARD && c->shadowOn && c->params.shadow_mode != FGL_SHADOW_HARD;
     int  rc = fgl_run_raster(c, P, planes_dev(c), nullptr, stochasticForward ? nullptr : &L);
     c->flushedPrims = c->primCounter;
-    c->frameRgb8Valid = false;
+    c->frameRgb8Valid = c->bandRgb8Valid = false;
     if (rc || !stochasticForward) return rc;
     // Forward + PCF / PCSS: every fragment that passed the depth test when it was submitted consumed samples, so the
     // winners' stream positions depend on all of them.  (Exact for a pass flushed once, which is how Render::DoForwardPass
@@ -292,6 +311,18 @@ int flush(fgl_ctx* c)
     if (nSites)
         if ((rc = fgl_stream_site_visibility(c, L, nSites, sc4, 0, nSites, 0))) return rc;
     return fgl_run_resolve_forward(c, P, planes_dev(c), L);
+}
+
+// A raster pass that ends without a single triangle still consumed the InitDepthBuffer issued for it (the reference's
+// depth buffer was re-created): its winner-id plane is empty, and the next pass must not inherit the pending re-init.
+void retire_empty_pass(fgl_ctx* c)
+{
+    if (!c->depthInitBound) return;
+    c->depthInitBound = false;
+    if (c->primCounter != 0 || !c->depthInitPending) return;
+    if (c->pass == FGL_PASS_LIGHTING) return;
+    (c->pass == FGL_PASS_SHADOW ? c->visLightClear : c->visCamClear) = true;
+    c->depthInitPending = false;
 }
 
 int ensure_rgb8(fgl_ctx* c)
@@ -369,6 +400,7 @@ void fgl_destroy(fgl_ctx* c)
     for (auto& v : c->vertices) release(v.pos), release(v.uv), release(v.nrm), release(v.tan);
     for (auto& m : c->meshes) release(m.pi), release(m.ti), release(m.ni);
     for (auto& t : c->timings) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+    for (auto& e : c->eventPool) cudaEventDestroy(e);
     cudaStreamDestroy(c->ownStream);
     delete c;
 }
@@ -407,6 +439,7 @@ static int upload(fgl_ctx* c, DevBuf& b, const void* src, size_t bytes)
 {
     if (int rc = fgl_reserve(c, b, std::max<size_t>(bytes, 16))) return rc;
     if (bytes) FGL_CUDA(c, cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    c->h2dBytes += bytes;
     return FGL_OK;
 }
 
@@ -469,13 +502,14 @@ int fgl_init_frame_buffer(fgl_ctx* c, int w, int h)
 {
     ENTER(c);
     if (int rc = flush(c)) return rc;
-    c->frameRgb8Valid = false;
+    c->frameRgb8Valid = c->bandRgb8Valid = false;
     return plane_init(c, FGL_PLANE_FRAME, w, h, 0.f);
 }
 int fgl_init_depth_buffer(fgl_ctx* c, int w, int h)
 {
     ENTER(c);
     if (int rc = flush(c)) return rc;
+    retire_empty_pass(c);
     c->depthInitPending = true;
     return plane_init(c, FGL_PLANE_DEPTH, w, h, FLT_MAX);
 }
@@ -505,7 +539,7 @@ int fgl_clear_color(fgl_ctx* c, const float rgb[3])
     if (!f.buf.p) return fgl_fail(c, FGL_ERR_STATE, "ClearColor before InitFrameBuffer");
     f.fillPending = true, f.fillIsRGB = true;
     memcpy(f.fillRGB, rgb, 12);
-    c->frameRgb8Valid = false;
+    c->frameRgb8Valid = c->bandRgb8Valid = false;
     return FGL_OK;
 }
 int fgl_set_viewport(fgl_ctx* c, int x, int y, int w, int h)  // forkergl.cpp:89-102
@@ -539,9 +573,12 @@ int fgl_set_pass_type(fgl_ctx* c, int pass)
     ENTER(c);
     if (pass < FGL_PASS_FORWARD || pass > FGL_PASS_SHADOW) return fgl_fail(c, FGL_ERR_INVALID, "bad pass type");
     if (int rc = flush(c)) return rc;
+    retire_empty_pass(c);
     c->pass = pass;
     c->primCounter = c->flushedPrims = 0;
     c->draws.clear();
+    c->passRestarted = true;
+    c->depthInitBound = c->depthInitPending;  // an InitDepthBuffer issued before SetPassType belongs to this pass
     return FGL_OK;
 }
 int fgl_set_shadow_status(fgl_ctx* c, int on)
@@ -560,6 +597,7 @@ int fgl_begin_frame(fgl_ctx* c)
         FGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->evChainDone, 0));
         c->chainEventPending = false;
     }
+    c->chainBlockersBefore = 0;  // a band's input is set after fgl_begin_frame, every frame (fgl_set_chain_blockers_before)
     fgl_stream_begin_frame(c);
     return FGL_OK;
 }
@@ -692,7 +730,7 @@ int fgl_prepare_screen_space_pixels(fgl_ctx* c, const float eye[3], const float 
     // that whatever the caller queues next on the main stream — SSAO, the blur — runs concurrently with it.
     static const bool noOverlap = getenv("FGL_NO_CHAIN_OVERLAP") != nullptr;
     // (per-kernel event timing is only meaningful without concurrency: the instrumented frames of bench.py run serially)
-    if (noOverlap || (c->timing && !fgl_stream_peer_on(c)) || !(fullBand || fgl_stream_peer_on(c))) return FGL_OK;
+    if (noOverlap || c->timing || !(fullBand || fgl_stream_peer_on(c))) return FGL_OK;
     if (!c->chainStream)
     {
         FGL_CUDA(c, cudaStreamCreateWithFlags(&c->chainStream, cudaStreamNonBlocking));
@@ -774,7 +812,7 @@ int fgl_blur(fgl_ctx* c, int plane, int kind)
     if (int rc = flush(c)) return rc;
     PlaneH& p = c->planes[plane];
     if (!p.buf.p) return fgl_fail(c, FGL_ERR_STATE, "fgl_blur: plane not initialised");
-    if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = false;
+    if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = c->bandRgb8Valid = false;
     int h0, h1, v0, v1;
     halo_band_of(c, p.h, h0, h1);
     if (int rc = kind == FGL_BLUR_TWO_PASS_GAUSSIAN ? materialize_rows(c, plane, h0, h1) : materialize(c, plane)) return rc;
@@ -793,6 +831,8 @@ int fgl_ssaa_resolve(fgl_ctx* c, int k)
     int r0, r1;
     band_of(c, f.h, r0, r1);
     bool fullBand = r0 == 0 && r1 == f.h;
+    if (!fullBand && (r0 % k != 0 || (r1 % k != 0 && r1 != f.h)))
+        return fgl_fail(c, FGL_ERR_INVALID, "fgl_ssaa_resolve: row band boundaries must be multiples of the SSAA kernel size");
     if (!(c->frameRgb8Valid || (!fullBand && c->bandRgb8Valid)))
         if (int rc = ensure_rgb8(c)) return rc;
     int ow = f.w / k, oh = f.h / k;
@@ -847,6 +887,12 @@ static int plane_as_aos(fgl_ctx* c, int plane, const void** src, size_t* bytes)
     size_t  n = (size_t)(cam ? c->visCamW : c->visLightW) * (cam ? c->visCamH : c->visLightH);
     *bytes = n * 4;
     if (!n) { *src = nullptr; return FGL_OK; }
+    bool& pendingClear = cam ? c->visCamClear : c->visLightClear;
+    if (pendingClear && vis.p)
+    {
+        FGL_CUDA(c, cudaMemsetAsync(vis.p, 0xFF, n * 8, c->stream));
+        pendingClear = false;
+    }
     if (int rc = fgl_reserve(c, c->scanTmp, n * 4)) return rc;
     if (int rc = fgl_run_ids(c, (const unsigned long long*)vis.p, n, (int*)c->scanTmp.p)) return rc;
     *src = c->scanTmp.p;
@@ -864,6 +910,7 @@ int fgl_read_plane(fgl_ctx* c, int plane, void* dst, size_t bytes)
     if (bytes != n) return fgl_fail(c, FGL_ERR_INVALID, "fgl_read_plane: size mismatch (have " + std::to_string(n) + ")");
     if (n) FGL_CUDA(c, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->d2hBytes += n;
     return FGL_OK;
 }
 
@@ -891,7 +938,8 @@ int fgl_write_plane(fgl_ctx* c, int plane, const void* src, size_t bytes)
     size_t  n = (size_t)p.w * p.h;
     if (!p.buf.p || bytes != n * p.ch * 4) return fgl_fail(c, FGL_ERR_INVALID, "fgl_write_plane: size mismatch");
     p.fillPending = false;
-    if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = false;
+    c->h2dBytes += bytes;
+    if (plane == FGL_PLANE_FRAME) c->frameRgb8Valid = c->bandRgb8Valid = false;
     if (p.ch == 1) FGL_CUDA(c, cudaMemcpyAsync(p.buf.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
     else
     {
@@ -933,7 +981,7 @@ int fgl_reset_timings(fgl_ctx* c)
 {
     ENTER(c);
     cudaStreamSynchronize(c->stream);
-    for (auto& t : c->timings) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
+    for (auto& t : c->timings) c->eventPool.push_back(t.e0), c->eventPool.push_back(t.e1);
     c->timings.clear();
     return FGL_OK;
 }
@@ -956,7 +1004,13 @@ int fgl_get_timings(fgl_ctx* c, FglTiming* out, int max, int* count)
             it = agg.emplace(t.name, f).first;
             order.push_back(t.name);
         }
-        it->second.ms_total += ms, it->second.launches += 1, it->second.algorithmic_bytes += t.bytes;
+        uint64_t bytes = t.bytes;
+        if (t.lateCount)
+        {   // byte figure that depends on a count the device produced (e.g. the PCSS entries that were actually filtered)
+            unsigned n = 0;
+            if (cudaMemcpy(&n, t.lateCount, 4, cudaMemcpyDeviceToHost) == cudaSuccess) bytes += (uint64_t)n * t.lateBytesEach;
+        }
+        it->second.ms_total += ms, it->second.launches += 1, it->second.algorithmic_bytes += bytes;
     }
     int n = 0;
     for (auto& name : order)
@@ -965,5 +1019,12 @@ int fgl_get_timings(fgl_ctx* c, FglTiming* out, int max, int* count)
     return FGL_OK;
 }
 int fgl_launch_count(fgl_ctx* c, uint64_t* o) { ENTER(c); if (o) *o = c->launches; return FGL_OK; }
+int fgl_transfer_bytes(fgl_ctx* c, uint64_t* h2d, uint64_t* d2h)
+{
+    ENTER(c);
+    if (h2d) *h2d = c->h2dBytes;
+    if (d2h) *d2h = c->d2hBytes;
+    return FGL_OK;
+}
 
 }  // extern "C"

@@ -122,6 +122,8 @@ struct TimingRec
     std::string name;
     cudaEvent_t e0, e1;
     uint64_t    bytes;
+    const unsigned* lateCount = nullptr;  // device counter read when the timings are fetched: bytes += *lateCount * lateBytesEach
+    uint64_t        lateBytesEach = 0;
 };
 
 struct fgl_ctx
@@ -147,7 +149,7 @@ struct fgl_ctx
     // visibility buffers (depth|primitive id keys)
     DevBuf visCamera, visLight;
     int    visCamW = 0, visCamH = 0, visLightW = 0, visLightH = 0;
-    bool   visCamClear = false, visLightClear = false, depthInitPending = false;
+    bool   visCamClear = false, visLightClear = false, depthInitPending = false, depthInitBound = false, passRestarted = false;
 
     // resources
     std::vector<TextureH>  textures;
@@ -172,7 +174,7 @@ struct fgl_ctx
     bool                   timing = false;
     std::vector<TimingRec> timings;
     std::vector<cudaEvent_t> eventPool;
-    uint64_t               launches = 0;
+    uint64_t               launches = 0, h2dBytes = 0, d2hBytes = 0;
     int                    lastUncertain = 0, lastChainIters = 0;  // PCSS: uncertain pixels / super-chunks of the last chain (diagnostics)
 };
 
@@ -187,21 +189,22 @@ int fgl_fail(fgl_ctx* c, int code, const std::string& msg);
     } while (0)
 
 int  fgl_reserve(fgl_ctx* c, DevBuf& b, size_t bytes);  // grow-only device allocation
-void fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes);
+bool fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes, const unsigned* lateCount, uint64_t lateBytesEach);
 void fgl_time_end(fgl_ctx* c);
 
 // RAII bracket used around every kernel launch: counts the launch and, when enabled, records CUDA events.
 struct LaunchScope
 {
     fgl_ctx* c;
-    LaunchScope(fgl_ctx* ctx, const char* name, uint64_t bytes) : c(ctx)
+    bool     recording = false;
+    LaunchScope(fgl_ctx* ctx, const char* name, uint64_t bytes, const unsigned* lateCount = nullptr, uint64_t lateBytesEach = 0) : c(ctx)
     {
         ++c->launches;
-        if (c->timing) fgl_time_begin(c, name, bytes);
+        if (c->timing) recording = fgl_time_begin(c, name, bytes, lateCount, lateBytesEach);
     }
     ~LaunchScope()
     {
-        if (c->timing) fgl_time_end(c);
+        if (recording) fgl_time_end(c);
     }
 };
 

@@ -696,6 +696,7 @@ int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t*
 
 int fgl_run_resolve_forward(fgl_ctx* c, const RasterPass& P, PlanesD planes, const LightPass& L)
 {
+    if (P.row1 <= P.row0) return FGL_OK;  // an empty band (more GPUs than rows)
     dim3        grid((P.W + 127) / 128, P.row1 - P.row0);
     LaunchScope ls(c, "resolve_forward", (uint64_t)P.W * (P.row1 - P.row0) * 24);
     k_resolve_forward<<<grid, 128, 0, c->stream>>>(P, planes, L);
@@ -758,7 +759,7 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
             LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88 + (uint64_t)P.W * (P.H - (P.row1 - P.row0)) * 12);
             k_resolve_geometry<<<dim3((P.W + 127) / 128, P.H), 128, 0, st>>>(P, planes);
         }
-        else if (P.passType == FGL_PASS_FORWARD && forwardLight)
+        else if (P.passType == FGL_PASS_FORWARD && forwardLight && P.row1 > P.row0)
         {
             LaunchScope ls(c, "resolve_forward", (uint64_t)P.W * (P.row1 - P.row0) * 24);
             k_resolve_forward<<<grid, 128, 0, st>>>(P, planes, *forwardLight);

@@ -503,6 +503,7 @@ int fgl_run_fill_rgb(fgl_ctx* c, float* dst, size_t nPixels, const float rgb[3])
 int fgl_run_lighting(fgl_ctx* c, const LightPass& L)
 {
     size_t   nPix = (size_t)L.W * (L.row1 - L.row0);
+    if (!nPix) return FGL_OK;  // an empty band
     uint64_t bytes = nPix * (80 + 3 + (L.writeF32 ? 12 : 0));
     {
         LaunchScope ls(c, "lighting", bytes + (L.vis ? nPix * 4 : 0));
@@ -548,6 +549,7 @@ int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind,
         return check_launch(c, "simple blur");
     }
     if (kind != FGL_BLUR_TWO_PASS_GAUSSIAN) return fgl_fail(c, FGL_ERR_INVALID, "fgl_blur: unknown blur kind");
+    if (hRow1 <= hRow0 || vRow1 <= vRow0) return FGL_OK;
     for (int ch = 0; ch < channels; ++ch)
     {
         {
@@ -565,6 +567,7 @@ int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind,
 int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S)
 {
     size_t      nPix = (size_t)S.W * (S.row1 - S.row0);
+    if (!nPix) return FGL_OK;
     LaunchScope ls(c, "ssao", nPix * (32 + 384));
     const float* m = S.viewport;  // ForkerGL::SetViewportMatrix structure (rows 0-2; the w row is not used by SSAO)
     const bool   affine = m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f;

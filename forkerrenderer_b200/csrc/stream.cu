@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot)
     if (valid) pilot[j] = (w >> lane) & 1u;
 }
 
-enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_ARRIVE = 4, CH_EPOCH = 5, CH_ERROR = 6, CH_ARRIVE_ROWS = 7, CH_NBLOCKERS = 8 };
+enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_ARRIVE = 4, CH_EPOCH = 5, CH_ERROR = 6, CH_ARRIVE_ROWS = 7, CH_NBLOCKERS = 8, CH_NFILTERED = 9 };
 
 // ---- the chain as ONE persistent cooperative kernel ----------------------------------------------------------------
 // A super-chunk is cut into segments of kSeg = 32 rows.  Per iteration (one super-chunk from an exactly known state):
@@ -972,6 +972,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+constexpr unsigned long long kPeerFailed = ~0ull;  // travels in place of a blocker count when a band's wait or chain failed
 __global__ void k_peer_wait(const unsigned long long* mailbox, unsigned long long epoch, unsigned long long* kDev, unsigned* err)
 {
     const unsigned long long* slot = mailbox + (epoch & 15ull) * 2;
@@ -985,12 +986,15 @@ __global__ void k_peer_wait(const unsigned long long* mailbox, unsigned long lon
             return;
         }
     }
-    *kDev = ld_acquire_sys_u64(slot + 1);
+    const unsigned long long v = ld_acquire_sys_u64(slot + 1);
+    if (v == kPeerFailed) *err = 2u, *kDev = 0ull;  // a band above gave up: pass the failure on instead of a count
+    else *kDev = v;
 }
 __global__ void k_peer_notify(unsigned long long* nextMailbox, unsigned long long epoch, const unsigned long long* kDev, const unsigned* state,
-                              unsigned long long hostBefore, unsigned nC1, int hasChain, unsigned long long* totalOut)
+                              unsigned long long hostBefore, unsigned nC1, int hasChain, unsigned long long* totalOut, const unsigned* err)
 {
     unsigned long long total = hostBefore + (kDev ? *kDev : 0ull) + nC1 + (hasChain ? (unsigned long long)state[CH_M0] : 0ull);
+    if (*err || (hasChain && (state[CH_ERROR] || !state[CH_DONE]))) total = kPeerFailed;
     *totalOut = total;
     if (nextMailbox)
     {
@@ -1025,11 +1029,10 @@ struct DeepShadow
     double       pcfFilter;
     float        areaLight;
 };
-__global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long long base, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis,
-                                                     unsigned* blockerList, unsigned* nBlockers, DeepShadow D, const unsigned long long* kDev)
+__device__ __forceinline__ bool chunk_index_pixel(size_t idx, size_t n, unsigned long long base, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis,
+                                                  unsigned* blockerList, unsigned* nBlockers, const DeepShadow& D, const unsigned long long* kDev)
 {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    bool filtered = false;
     if (kDev) base += 2ull * *kDev;
     chunkOf[idx] = (unsigned)(base + idx + 2ull * (unsigned)kpre[idx]);
     float v = 1.f;
@@ -1063,9 +1066,21 @@ __global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long lon
             }
         }
         blockerList[kpre[idx]] = entry;
+        filtered = entry != 0xffffffffu;
     }
     vis[idx] = v;
     if (idx == n - 1) *nBlockers = (unsigned)(kpre[idx] + hasB[idx]);
+    return filtered;
+}
+
+__global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long long base, const int* kpre, const int* hasB, unsigned* chunkOf, float* vis,
+                                                     unsigned* blockerList, unsigned* nBlockers, DeepShadow D, const unsigned long long* kDev, unsigned* nFiltered)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool   filtered = false;
+    if (idx < n) filtered = chunk_index_pixel(idx, n, base, kpre, hasB, chunkOf, vis, blockerList, nBlockers, D, kDev);
+    unsigned cnt = __popc(__ballot_sync(0xffffffffu, filtered));
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(nFiltered, cnt);
 }
 
 // shadow.cpp:47-63 for one pixel by one warp: 64 taps, two per lane; the sum of 1/64 steps is exact
@@ -1356,6 +1371,26 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     float*                   visB = (float*)s->vis.p + siteLo;
     const unsigned long long chunkBase = (unsigned long long)siteLo + 2ull * blockersBefore;
 
+    if (n == 0)
+    {   // an empty band (more GPUs than rows): no pixel consumes samples, the running blocker count passes through unchanged
+        s->prepValid = false, s->chainInFlight = false;
+        if (phase == FGL_VIS_PREPARE) return FGL_OK;
+        if (int rc = fgl_reserve(c, s->mState, 64)) return rc;
+        if (s->peerOn)
+        {
+            unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
+            FGL_CUDA(c, cudaMemsetAsync(loc, 0, 24, st));
+            if (s->peerWait)
+            {
+                LaunchScope ls(c, "pcss_peer_wait", 0);
+                k_peer_wait<<<1, 1, 0, st>>>((const unsigned long long*)s->mailbox.p, s->peerEpoch, loc, (unsigned*)(loc + 2));
+            }
+            LaunchScope ls(c, "pcss_peer_notify", 0);
+            k_peer_notify<<<1, 1, 0, st>>>(s->nextMailbox, s->peerEpoch, loc, (const unsigned*)s->mState.p, blockersBefore, 0u, 0, loc + 1, (const unsigned*)(loc + 2));
+        }
+        s->chainTotal = blockersBefore, s->chainCountValid = true, s->peerTotalOnDevice = s->peerOn;
+        return FGL_OK;
+    }
     // ---- PCSS chain --------------------------------------------------------------------------------------------
     size_t  smN = (size_t)L.sm.w * L.sm.h;
     DevBuf* f4[] = { &s->smTmpMin, &s->smTmpMax, &s->smMin, &s->smMax, &s->boxMin, &s->boxMax };
@@ -1428,6 +1463,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     if (int rc = scan_ints(c, (const int*)s->isC1.p, (int*)s->c1pre.p, n + 1)) return rc;
     FGL_CUDA(c, cudaMemcpyAsync(&nU, (int*)s->posU.p + n, 4, cudaMemcpyDeviceToHost, st));
     FGL_CUDA(c, cudaMemcpyAsync(&nC1, (int*)s->c1pre.p + n, 4, cudaMemcpyDeviceToHost, st));
+    c->d2hBytes += 8;
     FGL_CUDA(c, cudaStreamSynchronize(st));
     if (int rc = fgl_reserve(c, s->Upix, (size_t)(nU + 1) * 4)) return rc;
     if (int rc = fgl_reserve(c, s->Uc1, (size_t)(nU + 1) * 4)) return rc;
@@ -1483,12 +1519,12 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     if (s->peerOn)
     {   // blockers of the bands above arrive in this context's mailbox; rank 0 of the group (peerWait off) starts from zero
         unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
+        FGL_CUDA(c, cudaMemsetAsync(loc, 0, 24, st));  // count of the bands above, running total, error word: all per frame
         if (s->peerWait)
         {
             LaunchScope ls(c, "pcss_peer_wait", 0);
             k_peer_wait<<<1, 1, 0, st>>>((const unsigned long long*)s->mailbox.p, s->peerEpoch, loc, (unsigned*)(loc + 2));
         }
-        else FGL_CUDA(c, cudaMemsetAsync(loc, 0, 8, st));
     }
     if (nU > 0)
     {
@@ -1526,7 +1562,8 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
             uint32_t*      rowBits = (uint32_t*)s->rowBits.p;
             int*           rowLo = (int*)(rowBits + nRows * kChainNW);
             void*          args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter };
-            LaunchScope    ls(c, "pcss_chain", 0);
+            // algorithmic bytes: every uncertain row's record once (45 B) + every chunk signature of the band once (8 B)
+            LaunchScope    ls(c, "pcss_chain", (uint64_t)nU * 45 + ((uint64_t)n + 2ull * ((uint64_t)nC1 + (uint64_t)nU)) * 8);
             FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_chain_fused<kChainNW>, dim3(grid), dim3(1024), args, smemBytes, st));
         }
     }
@@ -1534,7 +1571,8 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     {   // the band below can start as soon as this band's chain has finished: signal it before anything else is queued
         unsigned long long* loc = (unsigned long long*)s->peerLocal.p;
         LaunchScope         ls(c, "pcss_peer_notify", 0);
-        k_peer_notify<<<1, 1, 0, st>>>(s->nextMailbox, s->peerEpoch, loc, (const unsigned*)s->mState.p, blockersBefore, (unsigned)nC1, nU > 0 ? 1 : 0, loc + 1);
+        k_peer_notify<<<1, 1, 0, st>>>(s->nextMailbox, s->peerEpoch, loc, (const unsigned*)s->mState.p, blockersBefore, (unsigned)nC1, nU > 0 ? 1 : 0, loc + 1,
+                                       (const unsigned*)(loc + 2));
     }
     }  // !inflight
     if (phase == FGL_VIS_LAUNCH)
@@ -1543,10 +1581,19 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         s->prepValid = true, s->prepTotal = nTotal, s->prepLo = siteLo, s->prepHi = siteHi, s->prepNU = nU, s->prepNC1 = nC1;
         return FGL_OK;
     }
+    if (s->peerOn)
+    {   // the wait for the band above may have timed out, or a band above may have failed: a wrong count must never be used silently
+        unsigned long long pl[3] = { 0, 0, 0 };
+        FGL_CUDA(c, cudaMemcpyAsync(pl, s->peerLocal.p, 24, cudaMemcpyDeviceToHost, st));
+        FGL_CUDA(c, cudaStreamSynchronize(st));
+        if (pl[2])
+            return fgl_fail(c, FGL_ERR_STATE, pl[2] == 1 ? "PCSS chain hand-off: the band above never signalled (30 s)" : "PCSS chain hand-off: a band above failed");
+    }
     if (nU > 0)
     {
         unsigned hs[8];
         FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 32, cudaMemcpyDeviceToHost, st));
+        c->d2hBytes += 32;
         FGL_CUDA(c, cudaStreamSynchronize(st));
         c->lastChainIters = (int)hs[CH_ITERS];
         uncertainBlockers = hs[CH_M0];
@@ -1570,11 +1617,13 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         DeepShadow D;
         D.isC1 = (const int*)s->isC1.p, D.sc4 = sc4In, D.smMin = (const float*)s->smMin.p, D.smMax = (const float*)s->smMax.p, D.sm = L.sm, D.r = r;
         D.pcfFilter = L.pcfFilter, D.areaLight = L.areaLight;
+        FGL_CUDA(c, cudaMemsetAsync((unsigned*)s->mState.p + CH_NFILTERED, 0, 4, st));
         k_chunk_index<<<nb, 256, 0, st>>>(n, chunkBase, (const int*)s->kpre.p, (const int*)s->hasB.p, chunkOfB, visB, (unsigned*)s->blockerList.p,
-                                          (unsigned*)s->mState.p + CH_NBLOCKERS, D, R.kDev);
+                                          (unsigned*)s->mState.p + CH_NBLOCKERS, D, R.kDev, (unsigned*)s->mState.p + CH_NFILTERED);
     }
     {
-        LaunchScope ls(c, "pcss_visibility", n / 2 * (16 + 8 + 768 + 4));
+        // bytes of the entries that are actually filtered (counted on the device by k_chunk_index): coordinate + chunk index + 96 samples + result
+        LaunchScope ls(c, "pcss_visibility", 0, (const unsigned*)s->mState.p + CH_NFILTERED, 16 + 4 + 768 + 4);
         k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
                                                    chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, visB);
     }
@@ -1661,6 +1710,11 @@ int fgl_stream_peer_connect(fgl_ctx* c, void* nextDevPtr, const void* nextIpcHan
     s->nextMailbox = nullptr, s->peerOn = false, s->peerWait = false;
     if (!enable) return FGL_OK;
     if (int rc = peer_buffers(c, s)) return rc;
+    // Epochs restart at 0 with every connect, so slots of an earlier session must not survive it.  The band above writes into
+    // this mailbox: every context of the group has to return from this call before any of them renders a frame (a group
+    // barrier; forkerrenderer_b200/multigpu.py and frh_group_connect have one).
+    FGL_CUDA(c, cudaMemset(s->mailbox.p, 0, 16 * 2 * 8));
+    FGL_CUDA(c, cudaMemset(s->peerLocal.p, 0, 64));
     if (nextIpcHandle64)
     {
         cudaIpcMemHandle_t h;

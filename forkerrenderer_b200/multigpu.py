@@ -49,8 +49,9 @@ class SyntheticRenderer:
 def setup_peer_handoff(fgl, dist, rank, world, height):
     """Connects the contexts of a sort-first group for the DEVICE-side chain hand-off (fgl_chain_peer_*): every rank
     publishes the CUDA IPC handle of its mailbox, opens the next rank's, and from then on waits / signals inside its
-    own stream.  Returns False (and leaves the host hand-off in place) if a band would be empty or IPC is not available."""
-    if world < 2 or band_rows(height, world, world - 1)[1] <= band_rows(height, world, world - 1)[0]:
+    own stream.  Returns False (and leaves the host hand-off in place) if IPC is not available on some rank.  Empty bands
+    (more GPUs than rows) take part like any other: their context waits for the count and passes it on."""
+    if world < 2:
         return False
     ok = True
     try:
@@ -83,13 +84,13 @@ def render_frame(r, rank, world, comm=None, band_out=None, peer=False):
     if r.pcss and peer:
         r.finish()
     elif r.pcss:
-        k = 0
-        if world > 1 and rank > 0 and r1 > r0:
-            k = comm.recv_int(rank - 1)
+        # every rank but the first receives, every rank but the last sends — also ranks whose band is empty (more GPUs than
+        # rows): they pass the running count on unchanged, so that every send has its matching receive
+        k = comm.recv_int(rank - 1) if world > 1 and rank > 0 else 0
         r.fgl.set_chain_blockers_before(k)
         r.finish()
         if world > 1 and rank < world - 1:
-            comm.send_int(r.fgl.get_chain_blockers() if r1 > r0 else 0, rank + 1)
+            comm.send_int(r.fgl.get_chain_blockers() if r1 > r0 else k, rank + 1)
     else:
         r.finish()
     if band_out is not None and r1 > r0:
@@ -130,3 +131,49 @@ def gather_bands(dist, torch, band_tensor, height, width, world):
     full = torch.empty((world * per, width, 3), dtype=torch.uint8, device=band_tensor.device)
     dist.all_gather_into_tensor(full, band_tensor)
     return full[:height]
+
+
+class Group:
+    """The sort-first group as bench.py drives it: one process per GPU, torch.distributed only for the rendezvous.
+
+    mode 'nccl': every GPU rasterises the whole shadow map, renders its band, the PCSS chain state travels through peer
+    mailboxes (or NCCL send / recv when IPC is unavailable) and the RGB8 bands are all-gathered with NCCL."""
+
+    def __init__(self, fgl, dist, rank, world, renderer, mode="nccl"):
+        import torch
+        self.torch, self.fgl, self.dist, self.rank, self.world, self.r, self.mode = torch, fgl, dist, rank, world, renderer, mode
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        H, W = renderer.height, renderer.width
+        self.r0, self.r1, self.per = band_rows(H, world, rank)
+        self.comm = TorchComm(dist, self.device)
+        self.peer = bool(renderer.pcss and setup_peer_handoff(fgl, dist, rank, world, H))
+        self.band = torch.empty((self.per, W, 3), dtype=torch.uint8, device=self.device)
+        self.full = None
+        self.host_frame = None
+        self.host_read_bytes = 0
+
+    def describe(self):
+        return ("sort-first row bands, %d rows per GPU, geometry and shadow pass replicated, RGB8 bands all-gathered with NCCL, PCSS chain state "
+                "handed on through %s" % (self.per, "peer memory (device-side wait)" if self.peer else "the host (NCCL send/recv)"))
+
+    def render_frame(self, gather=True):
+        render_frame(self.r, self.rank, self.world, self.comm, band_out=(self.band.data_ptr(), self.band.numel()), peer=self.peer)
+        if gather:
+            self.full = gather_bands(self.dist, self.torch, self.band, self.r.height, self.r.width, self.world)
+        return self.full
+
+    def read_frame(self):
+        """Rank 0: the gathered frame in page-locked host memory (numpy view); other ranks: waits for their stream."""
+        stream = self.torch.cuda.current_stream()
+        if self.rank != 0:
+            stream.synchronize()
+            return None
+        if self.host_frame is None:
+            self.host_frame = self.torch.empty(self.full.shape, dtype=self.torch.uint8, pin_memory=True)
+        self.host_frame.copy_(self.full, non_blocking=True)
+        stream.synchronize()
+        self.host_read_bytes = self.host_frame.numel()
+        return self.host_frame.numpy()
+
+    def close(self):
+        pass

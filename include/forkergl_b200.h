@@ -254,6 +254,9 @@ int fgl_reset_timings(fgl_ctx* ctx);
 int fgl_get_timings(fgl_ctx* ctx, FglTiming* out, int max, int* out_count);
 /* number of kernel launches issued by this library since ctx creation */
 int fgl_launch_count(fgl_ctx* ctx, uint64_t* out);
+/* bytes this library copied host -> device and device -> host since ctx creation (draw commands, texture tables, plane
+ * reads / writes, the few words of chain state): what a caller's frame really moves over PCIe */
+int fgl_transfer_bytes(fgl_ctx* ctx, uint64_t* out_host_to_device, uint64_t* out_device_to_host);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "mpixels_per_s" and d["unit"] == "Mpixels/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "sample" in d["config"]
+    assert set(d["config"]) == {"workload", "width", "height", "gpus"} and "sample" in d["cpu_baseline"]
+    assert (d["config"]["width"], d["config"]["height"]) == (1280, 800)
 
 
 def test_product_arm_needs_a_gpu():

@@ -32,6 +32,7 @@ class FakeFgl:
         self.log.append(("before", k))
 
     def get_chain_blockers(self):
+        assert self.band[1] > self.band[0], "an empty band has no chain to ask"
         return self.before + int(self.per_row[self.band[0]:self.band[1]].sum())
 
     def copy_plane_rows_to_device(self, plane, r0, r1, ptr, nbytes):
@@ -113,9 +114,9 @@ def peer_worker(rank, world, port, image, per_row, out):
             raise AssertionError("host hand-off used although peer=True")
         recv_int = send_int
     M.render_frame(r, rank, world, NoComm(), peer=True)
-    # a frame too short for the group (an empty last band) keeps the host hand-off
-    empty = M.setup_peer_handoff(PeerFgl(image, per_row), dist, rank, world, world - 2)
-    out.put((rank, (not mixed) and ok and wired and not empty))
+    # a frame too short for the group (an empty last band) is wired like any other
+    short = M.setup_peer_handoff(PeerFgl(image, per_row), dist, rank, world, world - 2)
+    out.put((rank, (not mixed) and ok and wired and short))
     dist.destroy_process_group()
 
 
@@ -146,10 +147,10 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_band_split_handoff_and_gather(world, oracle_fgl):
+@pytest.mark.parametrize("world,height", [(2, 50), (3, 50), (4, 6)])  # (4, 6): bands of 2 rows, the last band is empty
+def test_band_split_handoff_and_gather(world, height, oracle_fgl):
     s = SyntheticScene(oracle_fgl)
-    s.render(64, 50, shadow_mode=B.SHADOW_PCSS)
+    s.render(64, height, shadow_mode=B.SHADOW_PCSS)
     image = oracle_fgl.read_plane("frame_u8")
     rng = np.random.RandomState(1)
     per_row = rng.randint(0, 40, size=image.shape[0])
