@@ -370,6 +370,20 @@ class Host:
         self._ck(self.lib.frh_set_camera(scene.handle, (C.c_float * 3)(*eye), (C.c_float * 3)(*look_at)),
                  "frh_set_camera")
 
+    def test_fragments(self, scene, shadow_mode):
+        if isinstance(shadow_mode, str):
+            shadow_mode = SHADOW_MODES[shadow_mode]
+        cap = 1 << 16
+        out, n = (C.c_float * cap)(), C.c_int(0)
+        self.lib.frh_test_fragments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        self._ck(self.lib.frh_test_fragments(scene.handle, int(shadow_mode), out, cap, C.byref(n)), "frh_test_fragments")
+        assert n.value <= cap
+        return np.array(out[: n.value], dtype=np.float32)
+
+    def set_per_triangle_submission(self, on):
+        self.lib.frh_set_per_triangle_submission.restype = None
+        self.lib.frh_set_per_triangle_submission(int(bool(on)))
+
     def set_point_light(self, scene, position, color):
         self.lib.frh_set_point_light.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         self._ck(self.lib.frh_set_point_light(scene.handle, (C.c_float * 3)(*position), (C.c_float * 3)(*color)), "frh_set_point_light")

@@ -396,6 +396,7 @@ void fgl_destroy(fgl_ctx* c)
     for (auto& p : c->planes) release(p.buf);
     release(c->frameRgb8), release(c->ssaaRgb8), release(c->visCamera), release(c->visLight), release(c->texTable);
     release(c->drawsDev), release(c->setup), release(c->vary), release(c->zndc), release(c->nblk), release(c->blkScan), release(c->scanTmp);
+    for (auto& b : c->preChunks) release(b);
     for (auto& t : c->textures) release(t.data);
     for (auto& v : c->vertices) release(v.pos), release(v.uv), release(v.nrm), release(v.tan);
     for (auto& m : c->meshes) release(m.pi), release(m.ti), release(m.ni);
@@ -574,6 +575,15 @@ int fgl_set_pass_type(fgl_ctx* c, int pass)
     if (pass < FGL_PASS_FORWARD || pass > FGL_PASS_SHADOW) return fgl_fail(c, FGL_ERR_INVALID, "bad pass type");
     if (int rc = flush(c)) return rc;
     retire_empty_pass(c);
+    if (!c->preChunks.empty())
+    {   // arrays of fgl_draw_triangles: consumed by the flush above
+        FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i + 1 < c->preChunks.size(); ++i) release(c->preChunks[i]);
+        DevBuf last = c->preChunks.back();
+        c->preChunks.clear();
+        c->preChunks.push_back(last);
+        c->preUsed = 0;
+    }
     c->pass = pass;
     c->primCounter = c->flushedPrims = 0;
     c->draws.clear();
@@ -670,6 +680,56 @@ int fgl_draw_mesh(fgl_ctx* c, int meshId, int kind, const FglUniforms* un)
         }
     c->draws.push_back(d);
     c->primCounter += m.nFaces;
+    return FGL_OK;
+}
+
+// Device copy of a host array that has to stay alive until the pass ends (draws are deferred): chunks are only ever added
+// while a pass is open, so pointers already recorded in draw commands stay valid.
+static int stash(fgl_ctx* c, const float* src, size_t bytes, const float** out)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (c->preChunks.empty() || c->preUsed + bytes > c->preChunks.back().cap)
+    {
+        DevBuf b;
+        size_t want = std::max<size_t>(bytes, (size_t)8 << 20);
+        if (cudaMalloc(&b.p, want) != cudaSuccess) return fgl_fail(c, FGL_ERR_NOMEM, "cudaMalloc of " + std::to_string(want) + " bytes failed");
+        b.cap = want;
+        c->preChunks.push_back(b);
+        c->preUsed = 0;
+    }
+    char* dst = (char*)c->preChunks.back().p + c->preUsed;
+    FGL_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller's arrays may be gone when this call returns
+    c->h2dBytes += bytes;
+    c->preUsed += bytes;
+    *out = (const float*)dst;
+    return FGL_OK;
+}
+
+int fgl_draw_triangles(fgl_ctx* c, int meshId, int kind, const FglUniforms* un, int n, const float* ndc, const float* vary, const float* lightZ)
+{
+    ENTER(c);
+    if (!un || meshId < 0 || meshId >= (int)c->meshes.size() || n < 0 || (n && !ndc)) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: bad arguments");
+    if (kind < FGL_SHADER_DEPTH || kind > FGL_SHADER_PBR) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: bad shader kind");
+    if (c->pass == FGL_PASS_GEOMETRY && kind != FGL_SHADER_G)
+        return fgl_fail(c, FGL_ERR_STATE, "geometry pass requires GShader (reference forkergl.cpp:214 dynamic_cast)");
+    if (c->pass == FGL_PASS_SHADOW && kind != FGL_SHADER_DEPTH) return fgl_fail(c, FGL_ERR_STATE, "shadow pass requires DepthShader");
+    if (c->pass == FGL_PASS_FORWARD && kind != FGL_SHADER_BLINN_PHONG && kind != FGL_SHADER_PBR)
+        return fgl_fail(c, FGL_ERR_STATE, "forward pass requires BlinnPhongShader or PBRShader");
+    if (n && (kind == FGL_SHADER_DEPTH ? !lightZ : !vary)) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: the shader kind's per-triangle array is NULL");
+    if (n == 0) return FGL_OK;
+    if ((long long)c->primCounter + n > 0x7fffffffLL) return fgl_fail(c, FGL_ERR_INVALID, "too many triangles in one pass");
+    const MeshH& m = c->meshes[meshId];
+    DrawCmdD     d;
+    memset(&d, 0, sizeof d);
+    if (int rc = stash(c, ndc, (size_t)n * 48, &d.preNdc)) return rc;
+    if (kind == FGL_SHADER_DEPTH) { if (int rc = stash(c, lightZ, (size_t)n * 12, &d.preZ)) return rc; }
+    else if (int rc = stash(c, vary, (size_t)n * 192, &d.preVary)) return rc;
+    d.mat = m.mat, d.hasTangents = m.hasTangents, d.supportPBR = m.supportPBR, d.kind = kind;
+    d.firstPrim = c->primCounter, d.nFaces = n;
+    memcpy(d.lightPos, un->light_position, 12), memcpy(d.lightColor, un->light_color, 12), memcpy(d.eye, un->eye_position, 12);
+    c->draws.push_back(d);
+    c->primCounter += n;
     return FGL_OK;
 }
 

@@ -19,6 +19,8 @@ struct DrawCmdD
     float        model[16], view[16], proj[16], normal[9], lightSpace[16];
     float        lm[16];  // DepthShader: uLightSpaceMatrix * uModelMatrix (depthshader.h:23-24)
     float        lightPos[3], lightColor[3], eye[3];
+    // fgl_draw_triangles: the vertex programs ran on the host; per triangle 12 floats of NDC, 48 of varyings, 3 of light-space z
+    const float *preNdc, *preVary, *preZ;
 };
 
 // Per-triangle setup record, 48 bytes (three 16-byte words):
@@ -164,6 +166,8 @@ struct fgl_ctx
     int                   flushedPrims = 0;
     DevBuf                drawsDev, setup, vary, zndc, nblk, blkScan, scanTmp;
     DevBuf                fragCount, fragOffset, frags, nPass, passOff, siteOfPixel, siteKeys, siteVals, siteSc4, sortTmp;
+    std::vector<DevBuf>   preChunks;  // device copies of fgl_draw_triangles arrays, alive until the pass ends
+    size_t                preUsed = 0;
     void*                 pinned = nullptr;
     size_t                pinnedCap = 0;
 

@@ -76,6 +76,23 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
 #pragma unroll
         for (int i = 0; i < 48; ++i) vy.f[i] = 0.f;
     }
+    if (d.preNdc)
+    {   // fgl_draw_triangles: the caller ran the vertex program (Shader::ProcessVertex on the host)
+        const float* q = d.preNdc + (size_t)face * 12;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ndc[k].x = __ldg(q + 4 * k), ndc[k].y = __ldg(q + 4 * k + 1), ndc[k].z = __ldg(q + 4 * k + 2), ndc[k].w = __ldg(q + 4 * k + 3);
+        if (shadowPass)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) zn[k] = __ldg(d.preZ + (size_t)face * 3 + k);
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 48; ++i) vy.f[i] = __ldg(d.preVary + (size_t)face * 48 + i);
+        }
+    }
+    else
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {

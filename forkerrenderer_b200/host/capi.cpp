@@ -11,6 +11,7 @@
 #include "forkergl_b200.h"
 #include "output.h"
 #include "render.h"
+#include "shader.h"
 #include "shadow.h"
 
 static std::string s_Error;
@@ -111,6 +112,10 @@ int frh_set_point_light(void* scene, const float position[3], const float color[
     });
 }
 
+// Mesh::Draw face by face through Shader::ProcessVertex + ForkerGL::DrawTriangle (reference mesh.cpp:10-25) instead of one
+// indexed draw per mesh
+void frh_set_per_triangle_submission(int on) { ForkerGL::SetPerTriangleSubmission(on != 0); }
+
 // One frame: Render::Preconfigure + Render::Render (reference main.cpp:37-40).
 int frh_render(void* scene, int shadow_mode, int materialize_frame_f32)
 {
@@ -137,6 +142,69 @@ int frh_render_begin(void* scene, int shadow_mode, int materialize_frame_f32)
 int frh_render_finish(void* scene)
 {
     return Guard([&] { Render::RenderLightingStage(*(Scene*)scene); });
+}
+
+// Known-answer vectors of the HOST vertex + fragment programs (Shader::ProcessVertex / ProcessFragment, host/programs.cpp) in
+// the enumeration of `ref_driver --fragments`: after the shadow pass, every mesh of every model through GShader and its
+// model's forward program; faces 0, n/3, 2n/3 at three barycentric points; 19 words of GShader outputs / 3 of gl_Color each.
+int frh_test_fragments(void* scenePtr, int shadow_mode, float* out, int max, int* count)
+{
+    return Guard([&] {
+        Scene& scene = *(Scene*)scenePtr;
+        Shadow::SetShadowMode((Shadow::Mode)shadow_mode);
+        Shadow::ResetHostSampleStream();
+        Render::Preconfigure(scene);
+        fgl_ctx* ctx = ForkerGL::Context();
+        FglParams params = ForkerGL::Params();
+        params.shadow_mode = shadow_mode;
+        ForkerGL::Check(fgl_set_params(ctx, &params), "params");
+        ForkerGL::Check(fgl_set_shadow_status(ctx, Shadow::GetShadowStatus() ? 1 : 0), "shadow status");
+        ForkerGL::Check(fgl_begin_frame(ctx), "begin frame");
+        Render::DoShadowPass(scene);
+        int  n = 0;
+        auto put = [&](float f) { if (n < max) out[n] = f; ++n; };
+        auto put3 = [&](const Vector3f& v) { put(v.x), put(v.y), put(v.z); };
+        Float      ratio = scene.GetRatio();
+        Matrix4x4f view = scene.GetCamera().GetViewMatrix();
+        Matrix4x4f proj = scene.GetProjectionType() == Camera::Orthographic
+                              ? scene.GetCamera().GetOrthographicMatrix(-1.f * ratio, 1.f * ratio, -1.f, 1.f, 0.01f, 20.f)
+                              : scene.GetCamera().GetPerspectiveMatrix(45.f, ratio, 0.01f, 20.f);
+        const Vector3f pts[3] = { Vector3f(1.f / 3, 1.f / 3, 1.f / 3), Vector3f(0.6f, 0.3f, 0.1f), Vector3f(0.05f, 0.15f, 0.8f) };
+        for (int i = 0; i < (int)scene.GetModelCount(); ++i)
+        {
+            const Model& model = scene.GetModel(i);
+            GShader      gs;
+            gs.uModelMatrix = scene.GetModelMatrix(i), gs.uViewMatrix = view, gs.uProjectionMatrix = proj;
+            gs.uNormalMatrix = MakeNormalMatrix(gs.uModelMatrix), gs.uLightSpaceMatrix = ForkerGL::GetLightSpaceMatrix();
+            BlinnPhongShader bp;
+            PBRShader        pb;
+            bp.uModelMatrix = pb.uModelMatrix = scene.GetModelMatrix(i), bp.uViewMatrix = pb.uViewMatrix = view;
+            bp.uProjectionMatrix = pb.uProjectionMatrix = proj, bp.uNormalMatrix = pb.uNormalMatrix = MakeNormalMatrix(bp.uModelMatrix);
+            bp.uPointLight = pb.uPointLight = scene.GetPointLight(), bp.uEyePos = pb.uEyePos = scene.GetCamera().GetPosition();
+            bp.uLightSpaceMatrix = pb.uLightSpaceMatrix = ForkerGL::GetLightSpaceMatrix();
+            Shader* programs[2] = { &gs, model.SupportPBR() ? (Shader*)&pb : (Shader*)&bp };
+            for (int pass = 0; pass < 2; ++pass)
+                for (auto& kv : model.Meshes())
+                {
+                    Shader&   sh = *programs[pass];
+                    const int nf = kv.second->NumFaces();
+                    for (int f = 0; f < nf; ++f)
+                    {
+                        if (!(f == 0 || f == nf / 3 || f == 2 * nf / 3)) continue;
+                        sh.Use(kv.second);
+                        for (int v = 0; v < 3; ++v) sh.ProcessVertex(f, v);
+                        for (const Vector3f& b : pts)
+                        {
+                            Color3 c(0.f);
+                            sh.ProcessFragment(b, c);
+                            if (pass == 0) put3(gs.outNormalWS), put3(gs.outPositionWS), put3(gs.outLightSpaceNDC), put3(gs.outAlbedo), put3(gs.outEmissive), put3(gs.outParam), put(gs.outShadingType);
+                            else put3(c);
+                        }
+                    }
+                }
+        }
+        *count = n;
+    });
 }
 
 // Output::* of the reference's main (main.cpp:43-52) into `dir`.

@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -24,8 +25,65 @@ TGAImage ForkerGL::AntiAliasedImage;
 static fgl_ctx*             s_Ctx = nullptr;
 static ForkerGL::RenderMode s_RenderMode = ForkerGL::Forward;
 
+// ---- DrawTriangle batching -------------------------------------------------------------------------------------------
+// Consecutive DrawTriangle calls with the same mesh, program and uniforms form one batch; anything else the caller does
+// goes through Context(), which flushes the batch first, so the device sees the triangles in call order.
+namespace
+{
+struct TriangleBatch
+{
+    int                meshId = -1, kind = -1;
+    FglUniforms        uniforms;
+    std::vector<float> ndc, varyings, lightZ;
+    bool               open = false;
+} s_Batch;
+bool s_PerTriangle = false, s_Flushing = false;
+}  // namespace
+
+void ForkerGL::SetPerTriangleSubmission(bool on) { s_PerTriangle = on; }
+bool ForkerGL::GetPerTriangleSubmission() { return s_PerTriangle; }
+
+void ForkerGL::FlushTriangles()
+{
+    if (!s_Batch.open || s_Flushing) return;
+    s_Flushing = true;
+    s_Batch.open = false;
+    const int n = (int)(s_Batch.ndc.size() / 12);
+    int       rc = fgl_draw_triangles(s_Ctx, s_Batch.meshId, s_Batch.kind, &s_Batch.uniforms, n, s_Batch.ndc.data(),
+                                      s_Batch.varyings.empty() ? nullptr : s_Batch.varyings.data(), s_Batch.lightZ.empty() ? nullptr : s_Batch.lightZ.data());
+    s_Batch.ndc.clear(), s_Batch.varyings.clear(), s_Batch.lightZ.clear();
+    s_Flushing = false;
+    Check(rc, "DrawTriangle");
+}
+
+void ForkerGL::DrawTriangle(const Point4f ndcVerts[3], Shader& shader)
+{
+    if (shader.Kind() < 0)
+        throw std::runtime_error("ForkerGL::DrawTriangle: only DepthShader, GShader, BlinnPhongShader and PBRShader have device "
+                                 "fragment programs (user-defined Shader subclasses are unsupported)");
+    if (!shader.mesh) throw std::runtime_error("ForkerGL::DrawTriangle: shader.Use(mesh) was not called");
+    FglUniforms u;
+    shader.FillUniforms(u);
+    const int meshId = shader.mesh->DeviceId(), kind = shader.Kind();  // (may upload the model: goes through Context())
+    if (s_Batch.open && (s_Batch.meshId != meshId || s_Batch.kind != kind || memcmp(&s_Batch.uniforms, &u, sizeof u) != 0)) FlushTriangles();
+    if (!s_Batch.open)
+    {
+        Context();
+        s_Batch.open = true, s_Batch.meshId = meshId, s_Batch.kind = kind, s_Batch.uniforms = u;
+        InvalidateHostMirrors();
+    }
+    for (int v = 0; v < 3; ++v)
+    {
+        const float q[4] = { ndcVerts[v].x, ndcVerts[v].y, ndcVerts[v].z, ndcVerts[v].w };
+        s_Batch.ndc.insert(s_Batch.ndc.end(), q, q + 4);
+    }
+    if (kind == FGL_SHADER_DEPTH) s_Batch.lightZ.insert(s_Batch.lightZ.end(), shader.lightZ, shader.lightZ + 3);
+    else s_Batch.varyings.insert(s_Batch.varyings.end(), shader.varyings, shader.varyings + 48);
+}
+
 fgl_ctx* ForkerGL::Context()
 {
+    if (s_Ctx && s_Batch.open && !s_Flushing) FlushTriangles();
     if (!s_Ctx)
     {
         const char* dev = getenv("FGL_DEVICE");
@@ -55,6 +113,7 @@ FglParams& ForkerGL::Params()
 
 void ForkerGL::Shutdown()
 {
+    s_Batch = TriangleBatch();
     if (s_Ctx) fgl_destroy(s_Ctx);
     s_Ctx = nullptr;
 }

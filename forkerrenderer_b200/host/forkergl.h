@@ -61,8 +61,17 @@ struct ForkerGL
     static RenderMode GetRenderMode();
     static void       SetPassType(enum PassType type);
 
-    // Rasterization.  DrawMesh is what Mesh::Draw calls (one indexed draw per mesh).
+    // Rasterization.  DrawTriangle is the reference's entry (forkergl.h:74): one triangle whose three NDC positions the caller
+    // obtained from shader.ProcessVertex; triangles are batched and reach the device at the next state change, draw of another
+    // kind or read-back (fgl_draw_triangles), primitive ids in call order.  DrawMesh is what Mesh::Draw calls by default: one
+    // indexed draw per mesh, vertex programs on the device.
+    static void DrawTriangle(const Point4f ndcVerts[3], Shader& shader);
     static void DrawMesh(const Mesh& mesh, Shader& shader);
+    // Mesh::Draw submits face by face through ProcessVertex + DrawTriangle (the reference's loop, mesh.cpp:10-25) instead of
+    // one DrawMesh per mesh.  Same image either way; off by default.
+    static void SetPerTriangleSubmission(bool on);
+    static bool GetPerTriangleSubmission();
+    static void FlushTriangles();  // hands a pending DrawTriangle batch to the device (implied by every other entry point)
     static void DrawScreenSpacePixels(const Scene& scene);
     static void PrepareScreenSpacePixels(const Scene& scene, bool ssaoFollows);  // optional, multi-GPU: see fgl_prepare_screen_space_pixels
 

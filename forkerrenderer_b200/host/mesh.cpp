@@ -6,11 +6,23 @@
 #include "shader.h"
 
 // Reference Mesh::Draw (mesh.cpp:10-25): per face { shader.Use; 3x ProcessVertex; ForkerGL::DrawTriangle }.
-// Here: one indexed draw of all faces, executed by the device vertex/raster kernels.
+// Default here: one indexed draw of all faces, vertex programs included, on the device.  With
+// ForkerGL::SetPerTriangleSubmission(true) the reference's loop runs as it stands (host vertex programs, batched DrawTriangle).
 void Mesh::Draw(Shader& shader) const
 {
-    shader.Use(shared_from_this());
-    ForkerGL::DrawMesh(*this, shader);
+    if (!ForkerGL::GetPerTriangleSubmission())
+    {
+        shader.Use(shared_from_this());
+        ForkerGL::DrawMesh(*this, shader);
+        return;
+    }
+    for (int f = 0; f < NumFaces(); ++f)
+    {
+        shader.Use(shared_from_this());
+        Point4f ndcCoords[3];
+        for (int v = 0; v < 3; ++v) ndcCoords[v] = shader.ProcessVertex(f, v);
+        ForkerGL::DrawTriangle(ndcCoords, shader);
+    }
 }
 
 Vector3f Mesh::Vert(int faceIdx, int vertIdx) const

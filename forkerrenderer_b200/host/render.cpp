@@ -61,12 +61,14 @@ void RenderGeometryStage(const Scene& scene)
         ForkerGL::PrepareScreenSpacePixels(scene, scene.IsSSAOOn());
         if (scene.IsSSAOOn()) DoSSAO(scene);
     }
+    ForkerGL::FlushTriangles();  // per-triangle submission: nothing stays behind in the host-side batch
 }
 
 void RenderLightingStage(const Scene& scene)
 {
     if (ForkerGL::GetRenderMode() != ForkerGL::Forward) ForkerGL::DrawScreenSpacePixels(scene);  // render.cpp:210
     DoSSAA(scene);
+    ForkerGL::FlushTriangles();
 }
 
 void Render(const Scene& scene)

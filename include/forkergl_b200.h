@@ -200,6 +200,20 @@ int fgl_get_chain_blockers(fgl_ctx* ctx, uint64_t* out_blockers);
  * pass is flushed: at the next fgl_set_pass_type / fgl_init_* / fgl_draw_screen_space_pixels / read / sync. */
 int fgl_draw_mesh(fgl_ctx* ctx, int mesh_id, int shader_kind, const FglUniforms* uniforms);
 
+/* ForkerGL::DrawTriangle (src/forkergl.h:74, src/forkergl.cpp:239-324) for a batch of triangles whose vertex programs the CALLER
+ * has already run (Shader::ProcessVertex, src/shaders/shader.h:28): what arrives is what the reference's DrawTriangle sees —
+ * the three NDC positions ProcessVertex returned — plus the varyings the shader object holds when ProcessFragment is called.
+ *   ndc        12 floats per triangle: x,y,z,w of vertex 0, 1, 2
+ *   varyings   camera programs (G / Blinn-Phong / PBR), 48 floats per triangle, every attribute already times 1/w_clip
+ *              (gshader.h:71-92): [0..8] world position (vertex-major: x,y,z of vertex 0, then 1, 2), [9..17] world normal,
+ *              [18..26] world tangent, [27..35] light-space NDC, [36..38] u, [39..41] v, [42..44] 1/w_clip, [45..47] unused.
+ *              NULL for DepthShader.
+ *   light_z    DepthShader only: 3 floats per triangle, the z row of vPositionNDC (depthshader.h:21-36); NULL otherwise
+ * mesh_id supplies the material and the owning model's flags; uniforms supplies light / eye for the forward programs.
+ * Primitive ids continue the pass's submission order, triangle by triangle; the arrays are copied during the call. */
+int fgl_draw_triangles(fgl_ctx* ctx, int mesh_id, int shader_kind, const FglUniforms* uniforms, int n_triangles, const float* ndc,
+                       const float* varyings, const float* light_z);
+
 /* ForkerGL::DrawScreenSpacePixels (src/forkergl.cpp:326-380), the deferred lighting loop. */
 int fgl_draw_screen_space_pixels(fgl_ctx* ctx, const float eye_position[3], const float light_position[3],
                                  const float light_color[3]);

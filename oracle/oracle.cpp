@@ -903,6 +903,45 @@ int fgl_draw_mesh(fgl_ctx* c, int meshId, int kind, const FglUniforms* un)  // m
     return FGL_OK;
 }
 
+// ForkerGL::DrawTriangle (forkergl.cpp:239-324) for triangles whose vertex programs the caller ran: same rasteriser and
+// fragment programs as above, the varyings come from the caller's arrays (layout: include/forkergl_b200.h)
+int fgl_draw_triangles(fgl_ctx* c, int meshId, int kind, const FglUniforms* un, int n, const float* ndc, const float* vary, const float* lightZ)
+{
+    if (!c || !un || meshId < 0 || meshId >= (int)c->meshes.size() || n < 0 || (n && !ndc)) return fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: bad arguments");
+    if (c->pass == FGL_PASS_GEOMETRY && kind != FGL_SHADER_G)
+        return fail(c, FGL_ERR_STATE, "geometry pass requires GShader (reference forkergl.cpp:214 dynamic_cast)");
+    if (n && (kind == FGL_SHADER_DEPTH ? !lightZ : !vary)) return fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: the shader kind's per-triangle array is NULL");
+    Draw d;
+    d.mesh = &c->meshes[meshId];
+    d.vb = &c->vertices[d.mesh->vertices];
+    d.un = *un;
+    d.kind = kind;
+    memset(d.lm, 0, sizeof d.lm);
+    for (int t = 0; t < n; ++t)
+    {
+        Varyings vy;
+        memset(&vy, 0, sizeof vy);
+        for (int k = 0; k < 3; ++k)
+        {
+            const float* q = ndc + (size_t)t * 12 + 4 * k;
+            vy.ndc[k] = V4{ q[0], q[1], q[2], q[3] };
+            if (kind == FGL_SHADER_DEPTH)
+            {
+                vy.depthNdc[k] = v3(q[0], q[1], lightZ[(size_t)t * 3 + k]);
+                continue;
+            }
+            const float* f = vary + (size_t)t * 48;
+            vy.posWS[k] = v3(f[3 * k], f[3 * k + 1], f[3 * k + 2]);
+            vy.nrmWS[k] = v3(f[9 + 3 * k], f[10 + 3 * k], f[11 + 3 * k]);
+            vy.tanWS[k] = v3(f[18 + 3 * k], f[19 + 3 * k], f[20 + 3 * k]);
+            vy.lightNDC[k] = v3(f[27 + 3 * k], f[28 + 3 * k], f[29 + 3 * k]);
+            vy.u[k] = f[36 + k], vy.v[k] = f[39 + k], vy.oow[k] = f[42 + k];
+        }
+        DrawTriangle(c, d, vy, c->primCounter++);
+    }
+    return FGL_OK;
+}
+
 // forkergl.cpp:326-380
 int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpos[3], const float lcol[3])
 {

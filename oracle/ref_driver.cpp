@@ -19,7 +19,10 @@
 #include <cstring>
 #include <string>
 
+#include "gshader.h"
 #include "output.h"
+#include "pbrshader.h"
+#include "phongshader.h"
 #include "render.h"
 #include "utility.h"
 
@@ -218,13 +221,84 @@ static int MatrixTest(int argc, const char* argv[])
     return 0;
 }
 
+// --fragments: known-answer vectors of the reference's own vertex + fragment programs.  After the shadow pass, every mesh of
+// every model goes through GShader and through the forward program of its model (BlinnPhongShader / PBRShader, uniforms as
+// in render.cpp:121-154, 176-191); on faces 0, n/3 and 2n/3 ProcessFragment is evaluated at three barycentric points and
+// the outputs are printed as hex words: 19 of GShader (normal, position, light-space NDC, albedo, emissive, param, type)
+// and the 3 of gl_Color.  A probe Shader drives the programs from inside Model::Render (the meshes are not public) and
+// returns a degenerate triangle, so nothing is rasterised.
+struct FragmentProbe : public Shader
+{
+    Shader*  inner = nullptr;
+    GShader* g = nullptr;
+    Point4f  ProcessVertex(int faceIdx, int vertIdx) override
+    {
+        inner->Use(mesh);
+        inner->ProcessVertex(faceIdx, vertIdx);
+        const int n = mesh->NumFaces();
+        if (vertIdx == 2 && (faceIdx == 0 || faceIdx == n / 3 || faceIdx == 2 * n / 3))
+        {
+            const Vector3f pts[3] = { Vector3f(1.f / 3, 1.f / 3, 1.f / 3), Vector3f(0.6f, 0.3f, 0.1f), Vector3f(0.05f, 0.15f, 0.8f) };
+            for (const Vector3f& b : pts)
+            {
+                Color3 c(0.f);
+                inner->ProcessFragment(b, c);
+                auto put = [](float f) {
+                    uint32_t u;
+                    memcpy(&u, &f, 4);
+                    printf("%08x ", u);
+                };
+                auto put3 = [&](const Vector3f& v) { put(v.x), put(v.y), put(v.z); };
+                if (g) put3(g->outNormalWS), put3(g->outPositionWS), put3(g->outLightSpaceNDC), put3(g->outAlbedo), put3(g->outEmissive), put3(g->outParam), put(g->outShadingType);
+                else put3(c);
+            }
+        }
+        return Point4f(0.f, 0.f, 0.f, 1.f);
+    }
+    bool ProcessFragment(const Vector3f&, Color3&) override { return false; }
+};
+
+static void FragmentTest(const Scene& scene)
+{
+    Render::Preconfigure(scene);
+    Render::DoShadowPass(scene);
+    ForkerGL::InitFrameBuffer(scene.GetWidth(), scene.GetHeight());
+    ForkerGL::InitDepthBuffer(scene.GetWidth(), scene.GetHeight());
+    ForkerGL::SetPassType(ForkerGL::ForwardPass);
+    Float      ratio = scene.GetRatio();
+    Matrix4x4f view = scene.GetCamera().GetViewMatrix();
+    Matrix4x4f proj = (scene.GetProjectionType() == Camera::Orthographic)
+                          ? scene.GetCamera().GetOrthographicMatrix(-1.f * ratio, 1.f * ratio, -1.f, 1.f, 0.01f, 20.f)
+                          : scene.GetCamera().GetPerspectiveMatrix(45.f, ratio, 0.01f, 20.f);
+    for (int i = 0; i < (int)scene.GetModelCount(); ++i)
+    {
+        const Model&  model = scene.GetModel(i);
+        FragmentProbe probe;
+        GShader       gs;
+        gs.uModelMatrix = scene.GetModelMatrix(i), gs.uViewMatrix = view, gs.uProjectionMatrix = proj;
+        gs.uNormalMatrix = MakeNormalMatrix(gs.uModelMatrix), gs.uLightSpaceMatrix = ForkerGL::GetLightSpaceMatrix();
+        probe.inner = &gs, probe.g = &gs;
+        model.Render(probe);
+        probe.g = nullptr;
+        BlinnPhongShader bp;
+        PBRShader        pb;
+        bp.uModelMatrix = pb.uModelMatrix = scene.GetModelMatrix(i), bp.uViewMatrix = pb.uViewMatrix = view;
+        bp.uProjectionMatrix = pb.uProjectionMatrix = proj, bp.uNormalMatrix = pb.uNormalMatrix = MakeNormalMatrix(bp.uModelMatrix);
+        bp.uPointLight = pb.uPointLight = scene.GetPointLight(), bp.uEyePos = pb.uEyePos = scene.GetCamera().GetPosition();
+        bp.uLightSpaceMatrix = pb.uLightSpaceMatrix = ForkerGL::GetLightSpaceMatrix();
+        probe.inner = model.SupportPBR() ? (Shader*)&pb : (Shader*)&bp;
+        model.Render(probe);
+    }
+    printf("\n");
+}
+
 int main(int argc, const char* argv[])
 {
     if (argc == 3 && std::string(argv[1]) == "--buffer-test") return BufferTest(argv[2]);
     if (argc >= 2 && std::string(argv[1]) == "--matrices") return MatrixTest(argc, argv);
     std::string assets = ".", sceneFile, out = ".", shadow = "pcss";
     int         wrap = 0, filter = 0, frames = 1;
-    bool        ids = false, tga = false, quiet = false;
+    bool        ids = false, tga = false, quiet = false, fragments = false;
     for (int i = 1; i < argc; ++i)
     {
         std::string a = argv[i];
@@ -238,6 +312,7 @@ int main(int argc, const char* argv[])
         else if (a == "--frames") frames = atoi(next().c_str());
         else if (a == "--ids") ids = true;
         else if (a == "--tga") tga = true;
+        else if (a == "--fragments") fragments = true;
         else if (a == "--quiet") quiet = true;
         else
         {
@@ -273,6 +348,11 @@ int main(int argc, const char* argv[])
     double t0 = Now();
     Scene  scene(sceneFile);
     double tLoad = Now() - t0;
+    if (fragments)
+    {
+        FragmentTest(scene);
+        return 0;
+    }
 
     // Render::Preconfigure (render.cpp:33-38) also resets the texture-mode statics to NoWrap/Nearest; that
     // has no effect on already-loaded textures (fact 9) and is kept as is.

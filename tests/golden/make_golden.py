@@ -29,7 +29,11 @@ def fingerprint(a):
 def main():
     out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_hashes.json")
     golden = json.load(open(out_path)) if os.path.exists(out_path) else {}
-    cfgs = sys.argv[1:] or (list(P.CONFIGS) + ["buffer_ops", "host_math", "tga_files"])
+    cfgs = sys.argv[1:] or (list(P.CONFIGS) + ["buffer_ops", "host_math", "tga_files", "fragments"])
+    if "fragments" in cfgs:  # the reference's own Shader::ProcessVertex / ProcessFragment on selected faces (ref_driver --fragments)
+        cfgs.remove("fragments")
+        golden["fragments"] = {case: ["%08x" % w for w in P.run_reference_fragments(case)] for case in P.FRAGMENT_CASES}
+        print("fragments ok", flush=True)
     if "host_math" in cfgs:  # the reference's host uniform builders (geometry.cpp:60-68,92-179), words as hex
         cfgs.remove("host_math")
         golden["host_math"] = [{"case": [float(np.float32(v)) for v in case], "words": ["%08x" % w for w in P.run_reference_matrices(case)]}

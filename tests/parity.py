@@ -92,6 +92,22 @@ def run_reference_matrices(case):
     return np.array([int(w, 16) for w in r.stdout.split()], dtype=np.uint32)
 
 
+# known-answer vectors of the vertex + fragment programs (ref_driver --fragments / frh_test_fragments): scene, shadow, wrap, filter
+FRAGMENT_CASES = {
+    "pbr_ssao_pcss": ("scenes/pbr_ssao.scene", "pcss", 0, 0),
+    "c2_pcf": ("scenes/c2.scene", "pcf", 0, 0),
+    "c3_pbr_hard_repeat_linear": ("scenes/c3_pbr.scene", "hard", 1, 1),
+    "catbox_mirrored_linear": ("scenes/catbox.scene", "pcss", 2, 1),
+}
+
+
+def run_reference_fragments(case):
+    scene, shadow, wrap, filt = FRAGMENT_CASES[case]
+    r = subprocess.run([REF_DRIVER, "--assets", ASSETS, "--scene", os.path.join(REPO, scene), "--out", tempfile.gettempdir(), "--shadow", shadow,
+                        "--wrap", str(wrap), "--filter", str(filt), "--quiet", "--fragments"], check=True, stdout=subprocess.PIPE, text=True)
+    return np.array([int(w, 16) for w in r.stdout.split()], dtype=np.uint32)
+
+
 TGA_FILES = ["framebuffer.tga", "framebuffer_SSAA.tga", "shadowmap.tga", "zbuffer.tga", "gbuffer_normal.tga", "gbuffer_worldpos.tga",
              "gbuffer_albedo.tga", "gbuffer_param.tga", "gbuffer_shading_type.tga", "gbuffer_ambient_occlusion.tga"]
 

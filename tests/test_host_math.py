@@ -87,3 +87,37 @@ def test_camera_and_light_setters_equal_a_scene_file(oracle_host, golden):
             assert sha(f.read_plane(name)) == want[name]["sha256"], name
     finally:
         sc.free()
+
+
+@pytest.mark.parametrize("case", sorted(P.FRAGMENT_CASES))
+def test_host_shader_programs_match_the_reference(case, oracle_host, golden):
+    """Shader::ProcessVertex / ProcessFragment of the four programs on the host (host/programs.cpp), with Texture::Sample /
+    SampleFloat and Shadow::CalculateShadowVisibility (Hard / PCF / PCSS over the host's own mt19937 stream) behind them,
+    against the reference's own programs evaluated on the same faces and barycentric points (reference shader.h:28-30,
+    gshader.h, phongshader.h, pbrshader.h, texture.h:41-145, shadow.cpp:23-132): every output word, bit for bit."""
+    scene, shadow, wrap, filt = P.FRAGMENT_CASES[case]
+    sc = oracle_host.load_scene(os.path.join(P.REPO, scene), P.ASSETS, wrap, filt)
+    try:
+        got = oracle_host.test_fragments(sc, shadow).view(np.uint32)
+    finally:
+        sc.free()
+    want = np.array([int(w, 16) for w in golden["fragments"][case]], dtype=np.uint32)
+    assert got.shape == want.shape and len(want) > 100
+    assert np.array_equal(got, want), "words %s differ" % np.nonzero(got != want)[0][:16]
+
+
+def test_reference_mesh_draw_compiles_against_the_facade(tmp_path):
+    """The reference's Mesh::Draw (mesh.cpp:10-25: shader.Use, 3 x ProcessVertex, ForkerGL::DrawTriangle) is source-compatible
+    with the facade's headers.  Needs the reference sources (this container only)."""
+    src = "/root/reference/src/mesh.cpp"
+    if not os.path.exists(src):
+        pytest.skip("reference sources are not here")
+    import subprocess
+    body = "".join(open(src).readlines()[9:25])
+    assert "ProcessVertex" in body and "DrawTriangle" in body
+    tu = tmp_path / "ref_mesh_draw.cpp"
+    tu.write_text('#include "mesh.h"\n#include "forkergl.h"\n#include "shader.h"\n' + body)
+    host = os.path.join(P.REPO, "forkerrenderer_b200", "host")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I" + host, "-I" + os.path.join(P.REPO, "include"), str(tu)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
