@@ -373,6 +373,7 @@ int fgl_create(int device, fgl_ctx** out)
         return fgl_fail(nullptr, FGL_ERR_UNSUPPORTED, std::string("device ") + prop.name + " is not sm_100a (kernels are built for Blackwell only)");
     fgl_ctx* c = new fgl_ctx();
     c->device = device;
+    c->numSMs = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if ((e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking)) != cudaSuccess)
     {
         delete c;
@@ -793,7 +794,9 @@ int fgl_prepare_screen_space_pixels(fgl_ctx* c, const float eye[3], const float 
     if (noOverlap || c->timing || !(fullBand || fgl_stream_peer_on(c))) return FGL_OK;
     if (!c->chainStream)
     {
-        FGL_CUDA(c, cudaStreamCreateWithFlags(&c->chainStream, cudaStreamNonBlocking));
+        int prLo = 0, prHi = 0;  // the chain is the critical path of the frame: its CTAs are placed before anything else
+        cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+        FGL_CUDA(c, cudaStreamCreateWithPriority(&c->chainStream, cudaStreamNonBlocking, prHi));
         FGL_CUDA(c, cudaEventCreateWithFlags(&c->evChainGo, cudaEventDisableTiming));
         FGL_CUDA(c, cudaEventCreateWithFlags(&c->evChainDone, cudaEventDisableTiming));
     }

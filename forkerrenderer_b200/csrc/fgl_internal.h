@@ -130,7 +130,7 @@ struct TimingRec
 
 struct fgl_ctx
 {
-    int          device = 0;
+    int          device = 0, numSMs = 148;  // SM count of the device (persistent grids are sized in multiples of it)
     std::string  error;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     // the PCSS chain kernel runs on its own stream so that SSAO and the blur (main stream) overlap it
@@ -233,6 +233,7 @@ struct SsaoPass
     float        viewProj[16], viewport[16];
     float        radius, rangeCheckRadius, bias;
     int          rangeCheck;
+    int          backgroundIsOne;  // set by fgl_run_ssao: background pixels are exactly AO = 1 (see k_ssao)
     const float* ball;  // accepted unit-ball samples: x,y,z triples, 32 per pixel
 };
 int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S);

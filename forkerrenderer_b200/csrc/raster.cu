@@ -650,12 +650,12 @@ int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t*
         if (mode == RM_COUNT)
         {
             k_raster_small<RM_COUNT><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
-            k_raster_blocks<RM_COUNT><<<148 * 8, 256, 0, st>>>(P, 0, nPrims);
+            k_raster_blocks<RM_COUNT><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims);
         }
         else
         {
             k_raster_small<RM_FILL><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
-            k_raster_blocks<RM_FILL><<<148 * 8, 256, 0, st>>>(P, 0, nPrims);
+            k_raster_blocks<RM_FILL><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims);
         }
         ++c->launches;
     };
@@ -760,7 +760,7 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
         }
         {
             LaunchScope ls(c, "raster_blocks", 0);
-            k_raster_blocks<RM_DEPTH><<<148 * 8, 256, 0, st>>>(P, primBegin, nNew);
+            k_raster_blocks<RM_DEPTH><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew);
         }
     }
     if (P.passType == FGL_PASS_SHADOW)

@@ -4,6 +4,7 @@
 // layout conversions for the host accessors.
 #include <cuda_pipeline.h>
 
+#include <cmath>
 #include <cstdlib>
 
 #include "fgl_internal.h"
@@ -396,62 +397,86 @@ __global__ void __launch_bounds__(1024) k_simple_blur(float* a, int W, int H, in
 }
 
 // ---- SSAO, one warp per pixel: lane = hemisphere sample (render.cpp:229-285) -----------------------------------------
-// The kernel is bound by instruction issue (profiles/), so the arithmetic that cannot change the result is trimmed:
+// The kernel is bound by instruction issue (profiles/), so everything that cannot change the result is trimmed:
+//  * a warp walks kSsaoPPW consecutive pixels: the matrices, the viewport and the loop-invariant address arithmetic stay in
+//    registers instead of being re-fetched from the constant bank for every pixel; the next pixel's sample is loaded while
+//    the current one is being projected.
 //  * VIEWPORT_AFFINE: ForkerGL::SetViewportMatrix (forkergl.cpp:89-102) only fills [0][0], [0][3], [1][1], [1][3], [2][2],
 //    [2][3]; with finite x, y, z the reference's row products ((0 + m0 x) + m1 y) + m2 z) + m3 w reduce to
 //    (0 + m_k v_k) + m3 w bit for bit (adding 0 * finite = +-0 to a sum that is +0 or non-zero changes nothing), and
-//    the w row is never used.  Non-finite coordinates take the general product.
-//  * float -> int: cvttss2si only differs from a plain truncation outside +-2^31 (INT_MIN), checked once per sample.
+//    the w row is never used.  float -> int: cvttss2si only differs from a plain truncation outside +-2^31 (INT_MIN).
+//    Both shortcuts are taken by the whole warp or not at all (one vote per pixel instead of a branch per sample).
+//  * background pixels (nothing drawn: depth = FLT_MAX, position = normal = 0) with the range check on: every sample sits
+//    within the SSAO radius of the world origin; when the host has verified that the projection of that ball is finite
+//    (S.backgroundIsOne: |w_clip| bounded away from 0, see fgl_run_ssao) the sample's depth is finite, so
+//    "z >= cached + bias" fails against a cleared texel (FLT_MAX) and "|FLT_MAX - cached| < range" fails against a drawn
+//    one: the occlusion is exactly 0 and the pixel's AO exactly 1 without looking at a single sample.
+constexpr int kSsaoPPW = 4;
+
 template <bool VIEWPORT_AFFINE>
 __global__ void __launch_bounds__(256) k_ssao(SsaoPass S)
 {
     const unsigned n = (unsigned)S.W * (unsigned)S.H;  // planes have < 2^31 pixels (plane_init)
     const int      lane = threadIdx.x & 31;
-    const unsigned idx = (unsigned)S.row0 * (unsigned)S.W + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-    if (idx >= (unsigned)S.row1 * (unsigned)S.W) return;
-    const float* wp = S.worldpos + idx;
-    const float* np = S.normal + idx;
-    V3           pos = v3(wp[0], wp[n], wp[2 * (size_t)n]), nrm = v3(np[0], np[n], np[2 * (size_t)n]);
-    float        fragDepth = S.depth[idx];
+    const unsigned first = (unsigned)S.row0 * (unsigned)S.W + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSsaoPPW;
+    const unsigned end = (unsigned)S.row1 * (unsigned)S.W;
+    if (first >= end) return;
+    const unsigned last = min(first + kSsaoPPW, end);
+    const float    inf = __int_as_float(0x7f800000);
     // accepted unit-ball sample number 32 * pixel + lane of the replayed stream (geometry.h:957-966)
-    const float* b = S.ball + ((size_t)idx * 32 + lane) * 3;
-    V3           v = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
-    if (!(vdot(v, nrm) > 0.f)) v = v3(-v.x, -v.y, -v.z);  // geometry.h:978-990
-    float sc = vlength(v);
-    sc = (1 - 0.1f) * 1.0f + 0.1f * (sc * sc);  // Lerp(0.1f, 1.0f, sc * sc) with the reference's argument order
-    v = vscale(v, sc);
-    V3 sp = vadd(pos, vscale(v, S.radius));
-    V4 sp4;
-    sp4.x = sp.x, sp4.y = sp.y, sp4.z = sp.z, sp4.w = 1.f;
-    V4 cs = mat4mul(S.viewProj, sp4);
-    V4 ndc = vdivs4(cs, cs.w);
-    float ssx, ssy, ssz;
-    if (VIEWPORT_AFFINE && fabsf(ndc.x) < __int_as_float(0x7f800000) && fabsf(ndc.y) < __int_as_float(0x7f800000) && fabsf(ndc.z) < __int_as_float(0x7f800000))
+    const float* b = S.ball + ((size_t)first * 32 + lane) * 3;
+    V3           vNext = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
+    for (unsigned idx = first; idx < last; ++idx)
     {
-        ssx = (0.f + S.viewport[0] * ndc.x) + S.viewport[3] * ndc.w;
-        ssy = (0.f + S.viewport[5] * ndc.y) + S.viewport[7] * ndc.w;
-        ssz = (0.f + S.viewport[10] * ndc.z) + S.viewport[11] * ndc.w;
-    }
-    else
-    {
-        V4 ss = mat4mul(S.viewport, ndc);
-        ssx = ss.x, ssy = ss.y, ssz = ss.z;
-    }
-    int sx, sy;
-    if (fabsf(ssx) < 1.0e9f && fabsf(ssy) < 1.0e9f) sx = (int)ssx, sy = (int)ssy;
-    else sx = f2i_x86(ssx), sy = f2i_x86(ssy);
-    long long li = (long long)sx + (long long)sy * S.W;  // unchecked linear index in the reference (buffer.h:37)
-    bool      occ = false;
-    if (li >= 0 && li < (long long)n)
-    {
-        float cached = __ldg(S.depth + li);
-        if (ssz >= cached + S.bias) occ = S.rangeCheck ? (fabsf(fragDepth - cached) < S.rangeCheckRadius) : true;
-    }
-    int cnt = __popc(__ballot_sync(0xffffffffu, occ));
-    if (lane == 0)
-    {
-        float o = 1.f - (float)cnt * (1.f / 32.f);  // 1/32 steps accumulate exactly
-        S.ao[idx] = (o * o) * o;                    // pow(o, 3): k^3 / 32768 is exact in fp32
+        V3 v = vNext;
+        if (idx + 1 < last)
+        {
+            b += 96;
+            vNext = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
+        }
+        const float fragDepth = S.depth[idx];
+        const float* wp = S.worldpos + idx;
+        const V3     pos = v3(wp[0], wp[n], wp[2 * (size_t)n]);
+        if (S.backgroundIsOne && fragDepth >= 3.402823466e+38f && pos.x == 0.f && pos.y == 0.f && pos.z == 0.f)
+        {
+            if (lane == 0) S.ao[idx] = 1.f;
+            continue;
+        }
+        const float* np = S.normal + idx;
+        const V3     nrm = v3(np[0], np[n], np[2 * (size_t)n]);
+        if (!(vdot(v, nrm) > 0.f)) v = v3(-v.x, -v.y, -v.z);  // geometry.h:978-990
+        float sc = vlength(v);
+        sc = (1 - 0.1f) * 1.0f + 0.1f * (sc * sc);  // Lerp(0.1f, 1.0f, sc * sc) with the reference's argument order
+        v = vscale(v, sc);
+        V3 sp = vadd(pos, vscale(v, S.radius));
+        V4 sp4;
+        sp4.x = sp.x, sp4.y = sp.y, sp4.z = sp.z, sp4.w = 1.f;
+        V4 cs = mat4mul(S.viewProj, sp4);
+        V4 ndc = vdivs4(cs, cs.w);
+        float ssx = (0.f + S.viewport[0] * ndc.x) + S.viewport[3] * ndc.w;
+        float ssy = (0.f + S.viewport[5] * ndc.y) + S.viewport[7] * ndc.w;
+        float ssz = (0.f + S.viewport[10] * ndc.z) + S.viewport[11] * ndc.w;
+        int   sx = (int)ssx, sy = (int)ssy;
+        const bool plain = VIEWPORT_AFFINE && fabsf(ndc.x) < inf && fabsf(ndc.y) < inf && fabsf(ndc.z) < inf && fabsf(ssx) < 1.0e9f && fabsf(ssy) < 1.0e9f;
+        if (!__all_sync(0xffffffffu, plain))
+        {   // the general products and the x86 conversion, for every lane of the pixel
+            V4 ss = mat4mul(S.viewport, ndc);
+            ssx = ss.x, ssy = ss.y, ssz = ss.z;
+            sx = f2i_x86(ssx), sy = f2i_x86(ssy);
+        }
+        long long li = (long long)sx + (long long)sy * S.W;  // unchecked linear index in the reference (buffer.h:37)
+        bool      occ = false;
+        if (li >= 0 && li < (long long)n)
+        {
+            float cached = __ldg(S.depth + li);
+            if (ssz >= cached + S.bias) occ = S.rangeCheck ? (fabsf(fragDepth - cached) < S.rangeCheckRadius) : true;
+        }
+        int cnt = __popc(__ballot_sync(0xffffffffu, occ));
+        if (lane == 0)
+        {
+            float o = 1.f - (float)cnt * (1.f / 32.f);  // 1/32 steps accumulate exactly
+            S.ao[idx] = (o * o) * o;                    // pow(o, 3): k^3 / 32768 is exact in fp32
+        }
     }
 }
 
@@ -488,7 +513,7 @@ int fgl_run_fill(fgl_ctx* c, float* dst, size_t n, float value)
 {
     if (!n) return FGL_OK;
     LaunchScope ls(c, "fill", n * 4);
-    unsigned    blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    unsigned    blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->numSMs * 16);
     k_fill<<<blocks, 256, 0, c->stream>>>(dst, n, value);
     return check_launch(c, "fill");
 }
@@ -571,8 +596,27 @@ int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S)
     LaunchScope ls(c, "ssao", nPix * (32 + 384));
     const float* m = S.viewport;  // ForkerGL::SetViewportMatrix structure (rows 0-2; the w row is not used by SSAO)
     const bool   affine = m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f;
-    if (affine) k_ssao<true><<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(S);
-    else k_ssao<false><<<(unsigned)((nPix * 32 + 255) / 256), 256, 0, c->stream>>>(S);
+    // Background shortcut (see k_ssao): a sample of a background pixel lies within R = 1.0001 * radius of the world origin
+    // (|v| < 1, scale in [0.9, 1]).  Its clip-space w = (a, b, c) . P + d is at least |d| - R (|a| + |b| + |c|) in magnitude
+    // (less a rounding margin); if that is comfortably positive and every row of the matrix stays far from overflow, the
+    // projected point is finite — which is all the shortcut needs.
+    SsaoPass S2 = S;
+    {
+        const float* vp = S.viewProj;
+        const double R = 1.0001 * fabs((double)S.radius);
+        const double wMin = fabs((double)vp[15]) - R * (fabs((double)vp[12]) + fabs((double)vp[13]) + fabs((double)vp[14]));
+        double       rowMax = 0;
+        for (int r = 0; r < 3; ++r) rowMax = std::max(rowMax, fabs((double)vp[4 * r + 3]) + R * (fabs((double)vp[4 * r]) + fabs((double)vp[4 * r + 1]) + fabs((double)vp[4 * r + 2])));
+        double vpMax = 0;
+        for (int i = 0; i < 12; ++i) vpMax = std::max(vpMax, fabs((double)S.viewport[i]));
+        static const bool off = getenv("FGL_SSAO_NO_BG") != nullptr;
+        const bool finiteInputs = std::isfinite(wMin) && std::isfinite(rowMax) && std::isfinite(vpMax) && std::isfinite((double)S.bias);
+        S2.backgroundIsOne = !off && S.rangeCheck && S.rangeCheckRadius < 1.0e30f && finiteInputs && wMin > 1e-3 * (1.0 + fabs((double)vp[15])) &&
+                             (rowMax / wMin) * (1.0 + vpMax) * 4.0 < 1.0e30;
+    }
+    const unsigned warps = (unsigned)((nPix + kSsaoPPW - 1) / kSsaoPPW), blocks = (warps + 7) / 8;
+    if (affine) k_ssao<true><<<blocks, 256, 0, c->stream>>>(S2);
+    else k_ssao<false><<<blocks, 256, 0, c->stream>>>(S2);
     return check_launch(c, "ssao");
 }
 

@@ -562,6 +562,7 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int k)
     return pos;
 }
 
+constexpr int kMaxGrid = 160;              // CTAs (= SMs) the tables are sized for; a B200 has 148
 constexpr int kMaxSpc = 3;                 // segments one CTA evaluates per iteration
 constexpr int kRowsCta = kMaxSpc * kSeg;  // rows of those segments
 
@@ -570,7 +571,7 @@ template <int NW>
 struct ChainSmem
 {
     static constexpr int W = 32 * NW;
-    static constexpr int kMaxSegs = 148 * kMaxSpc;
+    static constexpr int kMaxSegs = kMaxGrid * kMaxSpc;
     // evaluation (every CTA)
     float4             rowS[kRowsCta];    // shadow coordinate + bias of the row
     unsigned long long rowE[kRowsCta];    // cells in which a tap can block
@@ -589,8 +590,8 @@ struct ChainSmem
 };
 
 template <int NW>
-__global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* state, const int* Ppre, uint8_t* G8all, uint32_t* GMall, int* segLoAll,
-                                                        uint32_t* rowBits, int* rowLo, uint8_t* flagU, int segsPerIter)
+__device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* state, const int* Ppre, uint8_t* G8all, uint32_t* GMall, int* segLoAll,
+                                                 uint32_t* rowBits, int* rowLo, uint8_t* flagU, int segsPerIter)
 {
     constexpr int W = 32 * NW;
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -954,6 +955,22 @@ __global__ void __launch_bounds__(1024, 1) k_chain_fused(ChainRows R, unsigned* 
     }
 }
 
+// The kernel proper, in builds that differ only in their register budget.  One CTA of 1024 threads per SM: at 64 registers it
+// owns the whole register file; the capped builds (48 / 40 / 32 registers) leave room for the blocks of the passes queued
+// on the main stream behind it — SSAO, the blur — to become resident next to it and fill the issue slots this
+// latency-bound kernel leaves empty (DESIGN.md §4 "Overlap").
+#define FGL_CHAIN_KERNEL(NAME, ATTR)                                                                                                          \
+    __global__ void ATTR NAME(ChainRows R, unsigned* state, const int* Ppre, uint8_t* G8all, uint32_t* GMall, int* segLoAll, uint32_t* rowBits, \
+                              int* rowLo, uint8_t* flagU, int segsPerIter)                                                                    \
+    {                                                                                                                                         \
+        chain_fused_body<kChainNW>(R, state, Ppre, G8all, GMall, segLoAll, rowBits, rowLo, flagU, segsPerIter);                               \
+    }
+FGL_CHAIN_KERNEL(k_chain_fused_r64, __launch_bounds__(1024, 1))
+FGL_CHAIN_KERNEL(k_chain_fused_r48, __maxnreg__(48))
+FGL_CHAIN_KERNEL(k_chain_fused_r40, __maxnreg__(40))
+FGL_CHAIN_KERNEL(k_chain_fused_r32, __launch_bounds__(1024, 2))
+#undef FGL_CHAIN_KERNEL
+
 // ---- device-side hand-off of the chain state between the bands of a sort-first group ----------------------------------
 // Band r + 1 needs the number of blockers found in bands 0..r.  Instead of a host round trip per band (stream sync, NCCL
 // send / recv, launch), the contexts exchange it through peer memory over NVLink: every context owns a mailbox of 16
@@ -1178,7 +1195,7 @@ struct SampleStream
     bool                peerOn = false, peerWait = false, peerTotalOnDevice = false;
     unsigned long long  peerEpoch = 0;
     // FGL_VIS_PREPARE -> FGL_VIS_RESOLVE hand-over
-    bool               prepValid = false, chainInFlight = false;
+    bool               prepValid = false, chainInFlight = false, chainWasShared = false;
     unsigned long long inflightBefore = 0;
     size_t             prepTotal = 0, prepLo = 0, prepHi = 0;
     int                prepNU = 0, prepNC1 = 0;
@@ -1319,6 +1336,66 @@ static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
     if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
     LaunchScope ls(c, "scan", n * 8);
     cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, in, out, (int)n, c->stream);
+    return FGL_OK;
+}
+
+// The persistent chain kernel: one CTA of 1024 threads per SM, grid-wide barriers on global counters.
+//   exclusive (shared = false): the 64-register build by a cooperative launch — co-residency guaranteed, the device is not
+//     shared with other kernels meanwhile;
+//   shared = true (the chain runs on its own stream while SSAO and the blur run on the main one): the 40-register build by a
+//     plain launch, so that the other passes' blocks become resident next to it.  Co-residency then follows from one CTA per
+//     SM being placed first (highest stream priority, issued ahead of SSAO); should a CTA ever be kept waiting beyond the
+//     barriers' time-outs the kernel reports an error and the caller re-runs the chain exclusively (see the RESOLVE phase).
+static int launch_chain(fgl_ctx* c, SampleStream* s, ChainRows& R, int nU, size_t n, int nC1, cudaStream_t st, bool shared)
+{
+    typedef void (*ChainKernel)(ChainRows, unsigned*, const int*, uint8_t*, uint32_t*, int*, uint32_t*, int*, uint8_t*, int);
+    static const int  segsEnv = getenv("FGL_CHAIN_SEGS") ? atoi(getenv("FGL_CHAIN_SEGS")) : 0;
+    static const int  regsEnv = getenv("FGL_CHAIN_REGS") ? atoi(getenv("FGL_CHAIN_REGS")) : 0;
+    static const int  coopEnv = getenv("FGL_CHAIN_COOP") ? atoi(getenv("FGL_CHAIN_COOP")) : -1;
+    static bool       ready = false;
+    const size_t      smemBytes = sizeof(ChainSmem<kChainNW>);
+    const ChainKernel all[4] = { k_chain_fused_r64, k_chain_fused_r48, k_chain_fused_r40, k_chain_fused_r32 };
+    if (!ready)
+    {
+        for (ChainKernel k : all)
+        {
+            int perSM = 0;
+            FGL_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+            FGL_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k, 1024, smemBytes));
+            if (perSM < 1) return fgl_fail(c, FGL_ERR_CUDA, "pcss chain: the persistent kernel does not fit an SM");
+        }
+        ready = true;
+    }
+    const int         regs = regsEnv ? regsEnv : (shared ? 40 : 64);
+    const bool        coop = coopEnv >= 0 ? coopEnv != 0 : !shared;
+    const ChainKernel kernel = regs <= 32 ? all[3] : regs <= 40 ? all[2] : regs <= 48 ? all[1] : all[0];
+    FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 64, st));
+    int grid = std::min(c->numSMs, kMaxGrid);  // one CTA per SM (kMaxSegs bounds the tables: at most kMaxGrid SMs)
+    int segsPerIter = segsEnv > 0 ? segsEnv : kMaxSpc * grid;
+    segsPerIter = std::max(1, std::min(segsPerIter, kMaxSpc * grid));
+    const size_t tw = (size_t)segsPerIter * 32 * kChainNW;
+    if (int rc = fgl_reserve(c, s->bits, 2 * tw * 5)) return rc;  // G8 (1 byte) + GM (4 bytes) per table entry, two parities
+    if (int rc = fgl_reserve(c, s->winLo, 2 * (size_t)segsPerIter * 4)) return rc;
+    uint8_t*     G8 = (uint8_t*)s->bits.p + 2 * tw * 4;
+    uint32_t*    GM = (uint32_t*)s->bits.p;
+    int*         segLo = (int*)s->winLo.p;
+    unsigned*    state = (unsigned*)s->mState.p;
+    const int*   Ppre = (const int*)s->Ppre.p;
+    uint8_t*     flagU = (uint8_t*)s->flagU.p;
+    const size_t nRows = (size_t)segsPerIter * 32;
+    if (int rc = fgl_reserve(c, s->rowBits, nRows * kChainNW * 4 + nRows * 4)) return rc;
+    uint32_t*    rowBits = (uint32_t*)s->rowBits.p;
+    int*         rowLo = (int*)(rowBits + nRows * kChainNW);
+    void*        args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter };
+    // algorithmic bytes: every uncertain row's record once (45 B) + every chunk signature of the band once (8 B)
+    LaunchScope ls(c, "pcss_chain", (uint64_t)nU * 45 + ((uint64_t)n + 2ull * ((uint64_t)nC1 + (uint64_t)nU)) * 8);
+    if (coop) FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(1024), args, smemBytes, st));
+    else
+    {
+        kernel<<<grid, 1024, smemBytes, st>>>(R, state, Ppre, G8, GM, segLo, rowBits, rowLo, flagU, segsPerIter);
+        FGL_CUDA(c, cudaGetLastError());
+    }
+    s->chainWasShared = shared;
     return FGL_OK;
 }
 
@@ -1532,40 +1609,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p;
         R.base = chunkBase;
         R.stats = s->chainStats.p && getenv("FGL_CHAIN_STATS") ? (unsigned long long*)s->chainStats.p : nullptr;
-        FGL_CUDA(c, cudaMemsetAsync(s->mState.p, 0, 64, st));
-        {
-            // persistent cooperative kernel: one CTA per SM, all co-resident (the launch fails otherwise)
-            static int nSM = 0, segsEnv = getenv("FGL_CHAIN_SEGS") ? atoi(getenv("FGL_CHAIN_SEGS")) : 0;
-            const size_t smemBytes = sizeof(ChainSmem<kChainNW>);
-            if (!nSM)
-            {
-                int perSM = 0;
-                FGL_CUDA(c, cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, c->device));
-                FGL_CUDA(c, cudaFuncSetAttribute(k_chain_fused<kChainNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-                FGL_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_chain_fused<kChainNW>, 1024, smemBytes));
-                if (perSM < 1) return fgl_fail(c, FGL_ERR_CUDA, "pcss chain: the persistent kernel does not fit an SM");
-            }
-            int grid = std::min(nSM, 148);
-            int segsPerIter = segsEnv > 0 ? segsEnv : kMaxSpc * grid;
-            segsPerIter = std::max(1, std::min(segsPerIter, kMaxSpc * grid));
-            const size_t tw = (size_t)segsPerIter * 32 * kChainNW;
-            if (int rc = fgl_reserve(c, s->bits, 2 * tw * 5)) return rc;  // G8 (1 byte) + GM (4 bytes) per table entry, two parities
-            if (int rc = fgl_reserve(c, s->winLo, 2 * (size_t)segsPerIter * 4)) return rc;
-            uint8_t*       G8 = (uint8_t*)s->bits.p + 2 * tw * 4;
-            uint32_t*      GM = (uint32_t*)s->bits.p;
-            int*           segLo = (int*)s->winLo.p;
-            unsigned*      state = (unsigned*)s->mState.p;
-            const int*     Ppre = (const int*)s->Ppre.p;
-            uint8_t*       flagU = (uint8_t*)s->flagU.p;
-            const size_t   nRows = (size_t)segsPerIter * 32;
-            if (int rc = fgl_reserve(c, s->rowBits, nRows * kChainNW * 4 + nRows * 4)) return rc;
-            uint32_t*      rowBits = (uint32_t*)s->rowBits.p;
-            int*           rowLo = (int*)(rowBits + nRows * kChainNW);
-            void*          args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter };
-            // algorithmic bytes: every uncertain row's record once (45 B) + every chunk signature of the band once (8 B)
-            LaunchScope    ls(c, "pcss_chain", (uint64_t)nU * 45 + ((uint64_t)n + 2ull * ((uint64_t)nC1 + (uint64_t)nU)) * 8);
-            FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_chain_fused<kChainNW>, dim3(grid), dim3(1024), args, smemBytes, st));
-        }
+        if (int rc = launch_chain(c, s, R, nU, n, nC1, st, /*shared=*/phase == FGL_VIS_LAUNCH)) return rc;
     }
     if (s->peerOn)
     {   // the band below can start as soon as this band's chain has finished: signal it before anything else is queued
@@ -1595,6 +1639,14 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 32, cudaMemcpyDeviceToHost, st));
         c->d2hBytes += 32;
         FGL_CUDA(c, cudaStreamSynchronize(st));
+        if ((hs[CH_ERROR] || !hs[CH_DONE]) && s->chainWasShared && !s->peerOn)
+        {   // a CTA of the shared (plain-launch) build was kept off its SM beyond the barriers' time-outs: once more, exclusively
+            R.nU = nU, R.Upix = (const unsigned*)s->Upix.p, R.Uc1 = (const unsigned*)s->Uc1.p, R.Usc = (const float4*)s->Usc.p;
+            R.UF = (const unsigned long long*)s->UF.p, R.UE = (const unsigned long long*)s->UE.p, R.base = chunkBase, R.stats = nullptr;
+            if (int rc = launch_chain(c, s, R, nU, n, nC1, st, false)) return rc;
+            FGL_CUDA(c, cudaMemcpyAsync(hs, s->mState.p, 32, cudaMemcpyDeviceToHost, st));
+            FGL_CUDA(c, cudaStreamSynchronize(st));
+        }
         c->lastChainIters = (int)hs[CH_ITERS];
         uncertainBlockers = hs[CH_M0];
         if (hs[CH_ERROR] || !hs[CH_DONE]) return fgl_fail(c, FGL_ERR_STATE, "PCSS chain: persistent kernel failed (code " + std::to_string(hs[CH_ERROR]) + ")");
@@ -1624,7 +1676,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     {
         // bytes of the entries that are actually filtered (counted on the device by k_chunk_index): coordinate + chunk index + 96 samples + result
         LaunchScope ls(c, "pcss_visibility", 0, (const unsigned*)s->mState.p + CH_NFILTERED, 16 + 4 + 768 + 4);
-        k_pcss_visibility<<<148 * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
+        k_pcss_visibility<<<c->numSMs * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
                                                    chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, visB);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
