@@ -370,6 +370,31 @@ class Host:
         self._ck(self.lib.frh_set_camera(scene.handle, (C.c_float * 3)(*eye), (C.c_float * 3)(*look_at)),
                  "frh_set_camera")
 
+    # ---- sort-first group (host/capi.cpp frh_group_*) ----
+    def group_export(self, scene):
+        n = self.lib.frh_group_member_bytes()
+        buf = C.create_string_buffer(n)
+        self.lib.frh_group_export.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self.lib.frh_group_export(scene.handle, buf), "frh_group_export")
+        return buf.raw
+
+    def group_connect(self, rank, world, members, same_process=False):
+        blob = b"".join(members)
+        assert len(blob) == world * self.lib.frh_group_member_bytes()
+        self.lib.frh_group_connect.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
+        self._ck(self.lib.frh_group_connect(int(rank), int(world), blob, int(bool(same_process))), "frh_group_connect")
+
+    def group_read_frame(self, height, width, out=None):
+        """Rank 0: the finished frame as a (height, width, 3) uint8 array in page-locked host memory."""
+        if out is None:
+            out = self.fgl.host_array((height, width, 3), np.uint8, key="group_frame")
+        self.lib.frh_group_read_frame.argtypes = [C.c_void_p, C.c_size_t]
+        self._ck(self.lib.frh_group_read_frame(out.ctypes.data_as(C.c_void_p), out.nbytes), "frh_group_read_frame")
+        return out
+
+    def group_disconnect(self):
+        self._ck(self.lib.frh_group_disconnect(), "frh_group_disconnect")
+
     def test_fragments(self, scene, shadow_mode):
         if isinstance(shadow_mode, str):
             shadow_mode = SHADOW_MODES[shadow_mode]

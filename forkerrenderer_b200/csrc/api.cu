@@ -124,6 +124,7 @@ int materialize_rows(fgl_ctx* c, int plane, int r0, int r1)
 
 void band_of(fgl_ctx* c, int H, int& r0, int& r1)
 {
+    if (c->group.on) return fgl_group_band(c, H, r0, r1);
     r0 = std::max(0, std::min(c->row0, H));
     r1 = c->row1 < 0 ? H : std::max(r0, std::min(c->row1, H));
 }
@@ -198,6 +199,31 @@ int flush(fgl_ctx* c)
     }
     P.passType = c->pass, P.shadowOn = c->shadowOn;
     memcpy(P.viewport, c->viewport, sizeof P.viewport);
+    P.cull0 = 0, P.cull1 = P.H, P.own0 = 0, P.own1 = 0, P.group = 0;
+    GroupState& grp = c->group;
+    if (grp.on)
+    {
+        if (c->pass == FGL_PASS_FORWARD)
+        {
+            c->flushedPrims = c->primCounter;
+            return fgl_fail(c, FGL_ERR_UNSUPPORTED, "a sort-first group renders deferred frames only");
+        }
+        if (P.W != grp.W || P.H != grp.H || c->planes[FGL_PLANE_SHADOW].buf.p != grp.expShadow || c->planes[FGL_PLANE_DEPTH].buf.p != grp.expDepth)
+        {
+            c->flushedPrims = c->primCounter;
+            return fgl_fail(c, FGL_ERR_STATE, "the frame does not have the size the group was connected for (fgl_group_export)");
+        }
+        if (c->primCounter != c->flushedPrims && c->flushedPrims != 0)
+        {
+            c->flushedPrims = c->primCounter;
+            return fgl_fail(c, FGL_ERR_UNSUPPORTED, "a sort-first group needs each raster pass submitted before it is flushed (one flush per pass)");
+        }
+        fgl_group_band(c, P.H, P.own0, P.own1);
+        if (shadowPass) P.row0 = P.own0, P.row1 = P.own1;  // this context's rows of the shadow map
+        P.cull0 = P.row0, P.cull1 = P.row1, P.group = 1;
+        P.peers.n = grp.world;
+        for (int r = 0; r < grp.world; ++r) P.peers.p[r] = shadowPass ? grp.peerShadow[r] : grp.peerDepth[r];
+    }
     size_t  nPix = (size_t)P.W * P.H;
     DevBuf& vis = shadowPass ? c->visLight : c->visCamera;
     bool&   visClear = shadowPass ? c->visLightClear : c->visCamClear;
@@ -216,7 +242,14 @@ int flush(fgl_ctx* c)
     c->passRestarted = false;
     if (int rc = fgl_reserve(c, vis, nPix * 8)) return rc;
     vw = P.W, vh = P.H;
-    if (visClear)
+    if (visClear && grp.on)
+    {   // only the rows this context rasterises (the others are never read: the resolves stay inside [cull0, cull1))
+        size_t rows = (size_t)(P.cull1 - P.cull0);
+        LaunchScope ls(c, "vis_clear", rows * P.W * 8);
+        if (rows) FGL_CUDA(c, cudaMemsetAsync((char*)vis.p + (size_t)P.cull0 * P.W * 8, 0xFF, rows * P.W * 8, c->stream));
+        visClear = true;  // (the rest of the buffer still holds old keys: a later stand-alone pass clears everything)
+    }
+    else if (visClear)
     {
         LaunchScope ls(c, "vis_clear", nPix * 8);
         FGL_CUDA(c, cudaMemsetAsync(vis.p, 0xFF, nPix * 8, c->stream));
@@ -301,6 +334,7 @@ int flush(fgl_ctx* c)
     int  rc = fgl_run_raster(c, P, planes_dev(c), nullptr, stochasticForward ? nullptr : &L);
     c->flushedPrims = c->primCounter;
     c->frameRgb8Valid = c->bandRgb8Valid = false;
+    if (!rc && grp.on) rc = fgl_group_signal(c, shadowPass ? FGL_GROUP_SHADOW : FGL_GROUP_DEPTH);
     if (rc || !stochasticForward) return rc;
     // Forward + PCF / PCSS: every fragment that passed the depth test when it was submitted consumed samples, so the
     // winners' stream positions depend on all of them.  (Exact for a pass flushed once, which is how Render::DoForwardPass
@@ -393,6 +427,8 @@ void fgl_destroy(fgl_ctx* c)
     if (c->chainStream) cudaStreamSynchronize(c->chainStream);
     cudaStreamSynchronize(c->stream);
     if (c->chainStream) cudaStreamDestroy(c->chainStream), cudaEventDestroy(c->evChainGo), cudaEventDestroy(c->evChainDone);
+    fgl_group_release(c);
+    release(c->group.flags);
     fgl_stream_destroy(c);
     for (auto& p : c->planes) release(p.buf);
     release(c->frameRgb8), release(c->ssaaRgb8), release(c->visCamera), release(c->visLight), release(c->texTable);
@@ -610,6 +646,15 @@ int fgl_begin_frame(fgl_ctx* c)
     }
     c->chainBlockersBefore = 0;  // a band's input is set after fgl_begin_frame, every frame (fgl_set_chain_blockers_before)
     fgl_stream_begin_frame(c);
+    if (c->group.on)
+    {   // the previous frame has been consumed here: the peers may store the next frame's rows into this context's planes
+        GroupState& g = c->group;
+        ++g.epoch;
+        g.readyWaited = g.shadowWaited = g.depthWaited = g.bandWaited = false;
+        // clears of the exchanged planes are never executed in a group: every row is written by the band that owns it
+        c->planes[FGL_PLANE_SHADOW].fillPending = c->planes[FGL_PLANE_DEPTH].fillPending = false;
+        return fgl_group_signal(c, FGL_GROUP_READY);
+    }
     return FGL_OK;
 }
 int fgl_set_chain_blockers_before(fgl_ctx* c, uint64_t blockers)
@@ -643,8 +688,130 @@ int fgl_set_row_band(fgl_ctx* c, int row0, int row1)
 {
     ENTER(c);
     if (row0 < 0 || (row1 >= 0 && row1 < row0)) return fgl_fail(c, FGL_ERR_INVALID, "bad row band");
+    if (c->group.on) return fgl_fail(c, FGL_ERR_STATE, "the row band of a context in a sort-first group follows from its rank (fgl_group_connect)");
     if (int rc = flush(c)) return rc;
     c->row0 = row0, c->row1 = row1;
+    return FGL_OK;
+}
+
+// ---- sort-first group --------------------------------------------------------------------------------------------------
+int fgl_group_export(fgl_ctx* c, int w, int h, FglGroupMember* out)
+{
+    ENTER(c);
+    if (!out || w <= 0 || h <= 0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_group_export: bad arguments");
+    if (int rc = flush(c)) return rc;
+    if (c->group.on) return fgl_fail(c, FGL_ERR_STATE, "fgl_group_export: disconnect the current group first");
+    memset(out, 0, sizeof *out);
+    // the exchanged planes get their final size now, so that their device addresses stay put
+    if (int rc = plane_init(c, FGL_PLANE_SHADOW, w, h, 0.f)) return rc;
+    if (int rc = plane_init(c, FGL_PLANE_DEPTH, w, h, FLT_MAX)) return rc;
+    if (int rc = fgl_reserve(c, c->frameRgb8, (size_t)w * h * 3 + 16)) return rc;
+    if (int rc = fgl_reserve(c, c->group.flags, sizeof(GroupFlagsD))) return rc;
+    FGL_CUDA(c, cudaMemset(c->group.flags.p, 0, sizeof(GroupFlagsD)));
+    void* chain = nullptr;
+    if (int rc = fgl_stream_peer_mailbox(c, &chain, out->chain_ipc)) return rc;
+    GroupState& g = c->group;
+    g.expShadow = c->planes[FGL_PLANE_SHADOW].buf.p, g.expDepth = c->planes[FGL_PLANE_DEPTH].buf.p, g.expRgb8 = c->frameRgb8.p;
+    g.W = w, g.H = h;
+    out->shadow_ptr = g.expShadow, out->depth_ptr = g.expDepth, out->frame_ptr = g.expRgb8, out->flags_ptr = g.flags.p, out->chain_ptr = chain;
+    out->width = w, out->height = h, out->device = c->device;
+    cudaIpcMemHandle_t hnd;
+    static_assert(sizeof hnd == 64, "CUDA IPC handles are 64 bytes");
+    FGL_CUDA(c, cudaIpcGetMemHandle(&hnd, g.expShadow));
+    memcpy(out->shadow_ipc, &hnd, 64);
+    FGL_CUDA(c, cudaIpcGetMemHandle(&hnd, g.expDepth));
+    memcpy(out->depth_ipc, &hnd, 64);
+    FGL_CUDA(c, cudaIpcGetMemHandle(&hnd, g.expRgb8));
+    memcpy(out->frame_ipc, &hnd, 64);
+    FGL_CUDA(c, cudaIpcGetMemHandle(&hnd, g.flags.p));
+    memcpy(out->flags_ipc, &hnd, 64);
+    return FGL_OK;
+}
+
+int fgl_group_connect(fgl_ctx* c, int rank, int world, const FglGroupMember* m, int sameProcess)
+{
+    ENTER(c);
+    if (!m || world < 1 || world > kMaxGroup || rank < 0 || rank >= world) return fgl_fail(c, FGL_ERR_INVALID, "fgl_group_connect: bad arguments");
+    if (int rc = flush(c)) return rc;
+    GroupState& g = c->group;
+    if (g.on) return fgl_fail(c, FGL_ERR_STATE, "fgl_group_connect: already connected");
+    if (!g.expShadow || m[rank].shadow_ptr != g.expShadow || m[rank].flags_ptr != g.flags.p)
+        return fgl_fail(c, FGL_ERR_STATE, "fgl_group_connect: members[rank] is not this context's fgl_group_export record");
+    for (int r = 0; r < world; ++r)
+        if (m[r].width != g.W || m[r].height != g.H) return fgl_fail(c, FGL_ERR_INVALID, "fgl_group_connect: the members were exported for different frame sizes");
+    auto map = [&](const unsigned char* ipc, void* ptr, int peerDevice, void** out) -> int {
+        if (sameProcess)
+        {
+            if (peerDevice != c->device)
+            {
+                cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fgl_fail(c, FGL_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            *out = ptr;
+            return FGL_OK;
+        }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, ipc, 64);
+        FGL_CUDA(c, cudaIpcOpenMemHandle(out, hnd, cudaIpcMemLazyEnablePeerAccess));
+        g.ipcMapped.push_back(*out);
+        return FGL_OK;
+    };
+    for (int r = 0; r < world; ++r)
+    {
+        if (r == rank)
+        {
+            g.peerShadow[r] = (float*)g.expShadow, g.peerDepth[r] = (float*)g.expDepth, g.peerFlags[r] = (GroupFlagsD*)g.flags.p;
+            continue;
+        }
+        void *a = nullptr, *b = nullptr, *f = nullptr;
+        if (int rc = map(m[r].shadow_ipc, m[r].shadow_ptr, m[r].device, &a)) return rc;
+        if (int rc = map(m[r].depth_ipc, m[r].depth_ptr, m[r].device, &b)) return rc;
+        if (int rc = map(m[r].flags_ipc, m[r].flags_ptr, m[r].device, &f)) return rc;
+        g.peerShadow[r] = (float*)a, g.peerDepth[r] = (float*)b, g.peerFlags[r] = (GroupFlagsD*)f;
+    }
+    if (rank == 0) g.rootRgb8 = (uint8_t*)g.expRgb8;
+    else
+    {
+        void* p = nullptr;
+        if (int rc = map(m[0].frame_ipc, m[0].frame_ptr, m[0].device, &p)) return rc;
+        g.rootRgb8 = (uint8_t*)p;
+    }
+    // the PCSS chain's blocker count travels band to band through the mailboxes of stream.cu
+    const bool last = rank == world - 1;
+    if (int rc = fgl_stream_peer_connect(c, last || !sameProcess ? nullptr : m[rank + 1].chain_ptr, last || sameProcess ? nullptr : m[rank + 1].chain_ipc, rank > 0, world > 1))
+        return rc;
+    g.rank = rank, g.world = world, g.epoch = 0, g.on = true;
+    c->row0 = 0, c->row1 = -1;
+    return FGL_OK;
+}
+
+int fgl_group_disconnect(fgl_ctx* c)
+{
+    ENTER(c);
+    if (int rc = flush(c)) return rc;
+    if (c->chainStream) FGL_CUDA(c, cudaStreamSynchronize(c->chainStream));
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    fgl_stream_peer_connect(c, nullptr, nullptr, 0, 0);
+    fgl_group_release(c);
+    c->visCamClear = c->visLightClear = true;
+    return FGL_OK;
+}
+
+int fgl_group_read_frame(fgl_ctx* c, void* dst, size_t bytes)
+{
+    ENTER(c);
+    GroupState& g = c->group;
+    if (!g.on || g.rank != 0) return fgl_fail(c, FGL_ERR_STATE, "fgl_group_read_frame: only rank 0 of a connected group holds the frame");
+    if (!dst || bytes != (size_t)g.W * g.H * 3) return fgl_fail(c, FGL_ERR_INVALID, "fgl_group_read_frame: size mismatch");
+    if (int rc = flush(c)) return rc;
+    if (int rc = fgl_group_wait(c, FGL_GROUP_BAND)) return rc;
+    FGL_CUDA(c, cudaMemcpyAsync(dst, g.expRgb8, bytes, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long err = 0;
+    FGL_CUDA(c, cudaMemcpyAsync(&err, &((GroupFlagsD*)g.flags.p)->error, 8, cudaMemcpyDeviceToHost, c->stream));
+    FGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->d2hBytes += bytes;
+    if (err) return fgl_fail(c, FGL_ERR_STATE, "sort-first group: a device-side wait for context " + std::to_string(err - 1) + " timed out (30 s)");
     return FGL_OK;
 }
 
@@ -759,7 +926,12 @@ static int build_light_pass(fgl_ctx* c, const float eye[3], const float lpos[3],
         if (!q.buf.p || q.w != frame.w || q.h != frame.h || !c->planes[FGL_PLANE_SHADOW].buf.p)
             return fgl_fail(c, FGL_ERR_STATE, "DrawScreenSpacePixels: shadows on without LightSpaceNDCPosGBuffer / ShadowBuffer");
         if (int rc = materialize_rows(c, FGL_PLANE_LIGHTNDC, L.row0, L.row1)) return rc;
-        if (int rc = materialize(c, FGL_PLANE_SHADOW)) return rc;
+        if (c->group.on)
+        {   // the other bands' rows of the shadow map arrive by peer stores
+            c->planes[FGL_PLANE_SHADOW].fillPending = false;
+            if (int rc = fgl_group_wait(c, FGL_GROUP_SHADOW)) return rc;
+        }
+        else if (int rc = materialize(c, FGL_PLANE_SHADOW)) return rc;
         L.sm = shadow_map_dev(c);
     }
     memcpy(L.eye, eye, 12), memcpy(L.lightPos, lpos, 12), memcpy(L.lightColor, lcol, 12);
@@ -827,6 +999,13 @@ int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpo
     size_t n = (size_t)L.W * L.H;
     if (int rc = fgl_reserve(c, c->frameRgb8, n * 3 + 16)) return rc;
     L.rgb8 = (uint8_t*)c->frameRgb8.p;
+    if (c->group.on)
+    {
+        if (c->frameRgb8.p != c->group.expRgb8 || L.W != c->group.W || L.H != c->group.H)
+            return fgl_fail(c, FGL_ERR_STATE, "the frame does not have the size the group was connected for (fgl_group_export)");
+        L.rgb8 = c->group.rootRgb8;  // the band's 8-bit rows go straight into rank 0's frame
+        if (int rc = fgl_group_wait(c, FGL_GROUP_READY)) return rc;
+    }
     if (c->chainEventPending)
     {   // a chain issued by fgl_prepare_screen_space_pixels: everything from here on is ordered behind it
         FGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->evChainDone, 0));
@@ -836,7 +1015,8 @@ int fgl_draw_screen_space_pixels(fgl_ctx* c, const float eye[3], const float lpo
         if (int rc = fgl_stream_prepare_lighting(c, L, FGL_VIS_RESOLVE)) return rc;  // continues a prepared chain, else does it all
     if (int rc = fgl_run_lighting(c, L)) return rc;
     c->frameRgb8Valid = fullBand;  // with a partial band only the band rows are current; readers take rows of the band
-    c->bandRgb8Valid = true;
+    c->bandRgb8Valid = !c->group.on;
+    if (c->group.on) return fgl_group_signal(c, FGL_GROUP_BAND, /*rootOnly=*/true);
     return FGL_OK;
 }
 
@@ -865,6 +1045,7 @@ int fgl_ssao(fgl_ctx* c)
     S.radius = c->params.ssao_radius, S.rangeCheckRadius = c->params.ssao_range_check_radius, S.bias = c->params.ssao_bias;
     S.rangeCheck = c->params.ssao_range_check;
     if (int rc = fgl_stream_prepare_ssao(c, S)) return rc;
+    if (int rc = fgl_group_wait(c, FGL_GROUP_DEPTH)) return rc;  // group: the other bands' depth rows arrive by peer stores
     return fgl_run_ssao(c, S);
 }
 
@@ -888,6 +1069,7 @@ int fgl_ssaa_resolve(fgl_ctx* c, int k)
 {
     ENTER(c);
     if (k < 1) return fgl_fail(c, FGL_ERR_INVALID, "fgl_ssaa_resolve: kernel size < 1");
+    if (c->group.on) return fgl_fail(c, FGL_ERR_UNSUPPORTED, "SSAA is not available in a sort-first group");
     if (int rc = flush(c)) return rc;
     const PlaneH& f = c->planes[FGL_PLANE_FRAME];
     if (!f.buf.p) return fgl_fail(c, FGL_ERR_STATE, "SSAA before InitFrameBuffer");

@@ -38,11 +38,55 @@ struct TriVary
     float f[48];
 };
 
+// grow-only device allocation
+struct DevBuf
+{
+    void*  p = nullptr;
+    size_t cap = 0;
+};
+
+// ---- sort-first group (one context per GPU of an NVLink box; include/forkergl_b200.h "fgl_group_*") ---------------------
+constexpr int kMaxGroup = 16;
+// where a kernel stores a band's rows: the same plane in every context of the group (this context included)
+struct PeerPlanes
+{
+    float* p[kMaxGroup];
+    int    n;
+};
+// one per context, in its own HBM; every peer stores the current frame number into ITS slot of the arrays (peer stores over
+// NVLink, system-scope release), the owner's wait kernels spin on them
+struct GroupFlagsD
+{
+    unsigned long long ready[kMaxGroup];   // peer r has begun frame e: this context's planes may receive frame e's rows from... (see group.cu)
+    unsigned long long shadow[kMaxGroup];  // peer r's rows of the shadow map of frame e have arrived
+    unsigned long long depth[kMaxGroup];   // peer r's rows of the camera depth plane of frame e have arrived
+    unsigned long long band[kMaxGroup];    // (rank 0 only) peer r's rows of the finished 8-bit frame e have arrived
+    unsigned long long error;              // a wait timed out
+};
+struct GroupState
+{
+    bool               on = false;
+    int                rank = 0, world = 1, W = 0, H = 0;
+    unsigned long long epoch = 0;
+    DevBuf             flags;  // this context's GroupFlagsD
+    GroupFlagsD*       peerFlags[kMaxGroup] = { nullptr };
+    float*             peerShadow[kMaxGroup] = { nullptr };
+    float*             peerDepth[kMaxGroup] = { nullptr };
+    uint8_t*           rootRgb8 = nullptr;  // rank 0's 8-bit frame
+    void *             expShadow = nullptr, *expDepth = nullptr, *expRgb8 = nullptr;  // what fgl_group_export handed out
+    std::vector<void*> ipcMapped;
+    bool               readyWaited = false, shadowWaited = false, depthWaited = false, bandWaited = false;  // per frame
+};
+
 struct RasterPass
 {
     // target
     int W, H, row0, row1;  // buffer size and the row band camera passes are restricted to
     int passType, shadowOn;
+    // sort-first group: only triangles that touch rows [cull0, cull1) are set up and rasterised (everything: 0, H);
+    // rows [own0, own1) of the pass's exchanged plane (shadow map / camera depth) are stored into every context of the group
+    int        cull0, cull1, own0, own1, group;
+    PeerPlanes peers;
     float viewport[16];
     // geometry
     const DrawCmdD* draws;
@@ -81,11 +125,6 @@ struct LightPass
 };
 
 // ---- host-side objects -----------------------------------------------------------------------------------
-struct DevBuf
-{
-    void*  p = nullptr;
-    size_t cap = 0;
-};
 
 struct PlaneH
 {
@@ -179,6 +218,7 @@ struct fgl_ctx
     std::vector<TimingRec> timings;
     std::vector<cudaEvent_t> eventPool;
     uint64_t               launches = 0, h2dBytes = 0, d2hBytes = 0;
+    GroupState             group;
     int                    lastUncertain = 0, lastChainIters = 0;  // PCSS: uncertain pixels / super-chunks of the last chain (diagnostics)
 };
 
@@ -211,6 +251,13 @@ struct LaunchScope
         if (recording) fgl_time_end(c);
     }
 };
+
+// sort-first group (group.cu)
+enum { FGL_GROUP_READY = 0, FGL_GROUP_SHADOW = 1, FGL_GROUP_DEPTH = 2, FGL_GROUP_BAND = 3 };
+int  fgl_group_signal(fgl_ctx* c, int what, bool rootOnly = false);  // store this frame's number into the peers' flag slots
+int  fgl_group_wait(fgl_ctx* c, int what);                           // device-side wait for every peer's slot (once per frame and kind)
+void fgl_group_band(const fgl_ctx* c, int H, int& r0, int& r1);
+void fgl_group_release(fgl_ctx* c);
 
 // kernels (raster.cu) ------------------------------------------------------------------------------------------
 int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb8, const LightPass* forwardLight);

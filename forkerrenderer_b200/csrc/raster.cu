@@ -68,14 +68,11 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
     int             face = prim - d.firstPrim;
     bool            shadowPass = P.passType == FGL_PASS_SHADOW;
 
-    V4       ndc[3];
-    TriVary  vy;
-    float    zn[3] = { 0.f, 0.f, 0.f };
-    if (!shadowPass)
-    {
-#pragma unroll
-        for (int i = 0; i < 48; ++i) vy.f[i] = 0.f;
-    }
+    // ---- positions first: clip space, viewport, integer snap, bounding box (forkergl.cpp:241-255) — enough to decide whether
+    // the triangle can touch this context's rows at all; the attributes follow only for the triangles that do
+    V4    ndc[3], ws[3];
+    float zn[3] = { 0.f, 0.f, 0.f }, oow[3] = { 0.f, 0.f, 0.f };
+    int   pidx[3] = { 0, 0, 0 };
     if (d.preNdc)
     {   // fgl_draw_triangles: the caller ran the vertex program (Shader::ProcessVertex on the host)
         const float* q = d.preNdc + (size_t)face * 12;
@@ -86,53 +83,30 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
 #pragma unroll
             for (int k = 0; k < 3; ++k) zn[k] = __ldg(d.preZ + (size_t)face * 3 + k);
         }
-        else
-        {
-#pragma unroll
-            for (int i = 0; i < 48; ++i) vy.f[i] = __ldg(d.preVary + (size_t)face * 48 + i);
-        }
     }
     else
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
     {
-        int pidx = __ldg(d.pi + face * 3 + k);
-        V3  p = ld3(d.pos, pidx);
-        V4  p4;
-        p4.x = p.x, p4.y = p.y, p4.z = p.z, p4.w = 1.f;
-        if (d.kind == FGL_SHADER_DEPTH)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
         {
-            V4 cs = mat4mul(d.lm, p4);
+            pidx[k] = __ldg(d.pi + face * 3 + k);
+            V3 p = ld3(d.pos, pidx[k]);
+            V4 p4;
+            p4.x = p.x, p4.y = p.y, p4.z = p.z, p4.w = 1.f;
+            if (d.kind == FGL_SHADER_DEPTH)
+            {
+                V4 cs = mat4mul(d.lm, p4);
+                ndc[k] = vdivs4(cs, cs.w);
+                zn[k] = ndc[k].z;
+                continue;
+            }
+            ws[k] = mat4mul(d.model, p4);
+            V4 vs = mat4mul(d.view, ws[k]);
+            V4 cs = mat4mul(d.proj, vs);
+            oow[k] = 1.f / cs.w;
             ndc[k] = vdivs4(cs, cs.w);
-            zn[k] = ndc[k].z;
-            continue;
         }
-        V4    ws = mat4mul(d.model, p4);
-        V4    vs = mat4mul(d.view, ws);
-        V4    cs = mat4mul(d.proj, vs);
-        int   tidx = __ldg(d.ti + face * 3 + k);
-        float tu = __ldg(d.uv + 2 * (size_t)tidx), tv = __ldg(d.uv + 2 * (size_t)tidx + 1);
-        V3    nWS = mat3mul(d.normal, vnormalize(ld3(d.nrm, __ldg(d.ni + face * 3 + k))));  // mesh.cpp:46-50
-        float oow = 1.f / cs.w;
-        vy.f[42 + k] = oow;
-        vy.f[0 + 3 * k] = ws.x * oow, vy.f[1 + 3 * k] = ws.y * oow, vy.f[2 + 3 * k] = ws.z * oow;
-        vy.f[36 + k] = tu * oow, vy.f[39 + k] = tv * oow;
-        vy.f[9 + 3 * k] = nWS.x * oow, vy.f[10 + 3 * k] = nWS.y * oow, vy.f[11 + 3 * k] = nWS.z * oow;
-        if (d.hasTangents)
-        {
-            V3 tWS = mat3mul(d.normal, vnormalize(ld3(d.tan, pidx)));
-            vy.f[18 + 3 * k] = tWS.x * oow, vy.f[19 + 3 * k] = tWS.y * oow, vy.f[20 + 3 * k] = tWS.z * oow;
-        }
-        if (P.shadowOn)
-        {
-            V4 ls = mat4mul(d.lightSpace, ws);
-            ls = vdivs4(ls, ls.w);
-            vy.f[27 + 3 * k] = ls.x * oow, vy.f[28 + 3 * k] = ls.y * oow, vy.f[29 + 3 * k] = ls.z * oow;
-        }
-        ndc[k] = vdivs4(cs, cs.w);
     }
-
-    // forkergl.cpp:241-255: viewport, integer snap, clamped bounding box
     int   X[3], Y[3];
     float dz[3];
 #pragma unroll
@@ -146,6 +120,8 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
     int mny = min(Y[0], min(Y[1], Y[2])), mxy = max(Y[0], max(Y[1], Y[2]));
     int xmin = clampi(mnx, 0, P.W - 1), xmax = clampi(mxx, 0, P.W - 1);
     int ymin = clampi(mny, 0, P.H - 1), ymax = clampi(mxy, 0, P.H - 1);
+    // sort-first group: the pixel loop of the reference (forkergl.cpp:165-171) restricted to this context's rows
+    ymin = max(ymin, P.cull0), ymax = min(ymax, P.cull1 - 1);
 
     TriCover tc = make_cover(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
     int      flags = 0;
@@ -153,6 +129,7 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
     if (!tc.valid) flags = TRI_SKIP;
     // a triangle whose own bounding box misses the buffer only scans pixels outside itself (all rejected)
     if (sane && (mxx < 0 || mnx > P.W - 1 || mxy < 0 || mny > P.H - 1)) flags = TRI_SKIP;
+    if (ymax < ymin) flags = TRI_SKIP;  // no row of this context's band
     int bw = xmax - xmin + 1, bh = ymax - ymin + 1, nb = 0;
     if (!(flags & TRI_SKIP))
     {
@@ -165,18 +142,57 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
         if (sane) flags |= 8;
     }
     P.nblk[prim] = nb;
-
     int4* so = reinterpret_cast<int4*>(P.setup + prim);
+    if (flags & TRI_SKIP)
+    {   // nothing else of a skipped triangle is ever read
+        so[2] = make_int4(0, 0, 0, flags);
+        return;
+    }
     so[0] = make_int4(X[0], X[1], X[2], Y[0]);
     so[1] = make_int4(Y[1], Y[2], __float_as_int(dz[0]), __float_as_int(dz[1]));
     so[2] = make_int4(__float_as_int(dz[2]), xmin | (xmax << 16), ymin | (ymax << 16), flags);
-    if (shadowPass) P.zndc[prim] = make_float4(zn[0], zn[1], zn[2], 0.f);
-    else if (!(flags & TRI_SKIP))
+    if (shadowPass)
     {
-        float4* vo = reinterpret_cast<float4*>(P.vary + prim);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) vo[i] = make_float4(vy.f[4 * i], vy.f[4 * i + 1], vy.f[4 * i + 2], vy.f[4 * i + 3]);
+        P.zndc[prim] = make_float4(zn[0], zn[1], zn[2], 0.f);
+        return;
     }
+    float4* vo = reinterpret_cast<float4*>(P.vary + prim);
+    if (d.preNdc)
+    {
+        const float4* q = reinterpret_cast<const float4*>(d.preVary + (size_t)face * 48);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) vo[i] = __ldg(q + i);
+        return;
+    }
+    // ---- attributes of the vertex program (gshader.h:41-92 == phongshader.h:35-85 == pbrshader.h:35-85), each times 1 / w_clip
+    TriVary vy;
+#pragma unroll
+    for (int i = 0; i < 48; ++i) vy.f[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        int   tidx = __ldg(d.ti + face * 3 + k);
+        float tu = __ldg(d.uv + 2 * (size_t)tidx), tv = __ldg(d.uv + 2 * (size_t)tidx + 1);
+        V3    nWS = mat3mul(d.normal, vnormalize(ld3(d.nrm, __ldg(d.ni + face * 3 + k))));  // mesh.cpp:46-50
+        float w = oow[k];
+        vy.f[42 + k] = w;
+        vy.f[0 + 3 * k] = ws[k].x * w, vy.f[1 + 3 * k] = ws[k].y * w, vy.f[2 + 3 * k] = ws[k].z * w;
+        vy.f[36 + k] = tu * w, vy.f[39 + k] = tv * w;
+        vy.f[9 + 3 * k] = nWS.x * w, vy.f[10 + 3 * k] = nWS.y * w, vy.f[11 + 3 * k] = nWS.z * w;
+        if (d.hasTangents)
+        {
+            V3 tWS = mat3mul(d.normal, vnormalize(ld3(d.tan, pidx[k])));
+            vy.f[18 + 3 * k] = tWS.x * w, vy.f[19 + 3 * k] = tWS.y * w, vy.f[20 + 3 * k] = tWS.z * w;
+        }
+        if (P.shadowOn)
+        {
+            V4 ls = mat4mul(d.lightSpace, ws[k]);
+            ls = vdivs4(ls, ls.w);
+            vy.f[27 + 3 * k] = ls.x * w, vy.f[28 + 3 * k] = ls.y * w, vy.f[29 + 3 * k] = ls.z * w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) vo[i] = make_float4(vy.f[4 * i], vy.f[4 * i + 1], vy.f[4 * i + 2], vy.f[4 * i + 3]);
 }
 
 // Exclusive scan of up to a few hundred thousand ints by one CTA (the two-kernel device-wide scan costs more in
@@ -349,8 +365,8 @@ __device__ __forceinline__ bool decode_winner(const RasterPass& P, size_t idx, i
 
 __global__ void __launch_bounds__(256) k_resolve_shadow(RasterPass P, float* shadowPlane, float* depthPlane)
 {
-    size_t n = (size_t)P.W * P.H;
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)P.row1 * P.W;  // rows [row0, row1): everything, or this context's rows of the map in a sort-first group
+    size_t idx = (size_t)P.row0 * P.W + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     int   px = (int)(idx % P.W), py = (int)(idx / P.W);
     int   prim;
@@ -362,8 +378,12 @@ __global__ void __launch_bounds__(256) k_resolve_shadow(RasterPass P, float* sha
         sh = interp(z.x, z.y, z.z, bary) * 0.5f + 0.5f;  // depthshader.h:30-36
     }
     else depth = 3.402823466e+38f;
-    shadowPlane[idx] = sh;
     depthPlane[idx] = depth;
+    if (!P.group) shadowPlane[idx] = sh;
+    else
+    {   // fused all-gather: the texel goes into every context's shadow map (peer stores over NVLink; [rank] is this context's own)
+        for (int r = 0; r < P.peers.n; ++r) P.peers.p[r][idx] = sh;
+    }
 }
 
 struct Surface
@@ -425,7 +445,7 @@ __device__ __forceinline__ void load_vary(const TriVary* vary, int prim, float* 
 // gshader.h:95-201 + the G-buffer writes of forkergl.cpp:211-223
 __global__ void __launch_bounds__(128) k_resolve_geometry(RasterPass P, PlanesD out)
 {
-    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = (P.group ? P.row0 : 0) + blockIdx.y;
     if (px >= P.W) return;
     size_t n = (size_t)P.W * P.H, idx = (size_t)px + (size_t)py * P.W;
     int    prim;
@@ -438,9 +458,16 @@ __global__ void __launch_bounds__(128) k_resolve_geometry(RasterPass P, PlanesD 
         out.p[FGL_PLANE_DEPTH][idx] = covered ? depth : 3.402823466e+38f;
         return;
     }
+    if (P.group)
+    {   // sort-first group: the depth plane is exchanged — rows of this context's own band go into every context's plane
+        // (halo rows are owned, and delivered, by the neighbouring band)
+        const float dv = covered ? depth : 3.402823466e+38f;
+        if (py >= P.own0 && py < P.own1)
+            for (int r = 0; r < P.peers.n; ++r) P.peers.p[r][idx] = dv;
+    }
     if (!covered)
     {
-        out.p[FGL_PLANE_DEPTH][idx] = 3.402823466e+38f;
+        if (!P.group) out.p[FGL_PLANE_DEPTH][idx] = 3.402823466e+38f;
         st3(out.p[FGL_PLANE_NORMAL], n, idx, z3);
         st3(out.p[FGL_PLANE_WORLDPOS], n, idx, z3);
         if (P.shadowOn) st3(out.p[FGL_PLANE_LIGHTNDC], n, idx, z3);
@@ -476,7 +503,7 @@ __global__ void __launch_bounds__(128) k_resolve_geometry(RasterPass P, PlanesD 
         param = v3(1.f, m.ks[0], shininess);
         type = 0.f;
     }
-    out.p[FGL_PLANE_DEPTH][idx] = depth;
+    if (!P.group) out.p[FGL_PLANE_DEPTH][idx] = depth;
     st3(out.p[FGL_PLANE_NORMAL], n, idx, s.normal);
     st3(out.p[FGL_PLANE_WORLDPOS], n, idx, s.posWS);
     if (P.shadowOn) st3(out.p[FGL_PLANE_LIGHTNDC], n, idx, s.lightNDC);
@@ -763,18 +790,24 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
             k_raster_blocks<RM_DEPTH><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew);
         }
     }
+    // sort-first group: the resolves store into the other contexts' planes — not before those have begun this frame
+    if (P.group)
+        if (int rc = fgl_group_wait(c, FGL_GROUP_READY)) return rc;
     if (P.passType == FGL_PASS_SHADOW)
     {
-        LaunchScope ls(c, "resolve_shadow", (uint64_t)nPix * 16);
-        k_resolve_shadow<<<(unsigned)((nPix + 255) / 256), 256, 0, st>>>(P, planes.p[FGL_PLANE_SHADOW], planes.p[FGL_PLANE_DEPTH]);
+        const size_t nBand = (size_t)P.W * (P.row1 - P.row0);
+        LaunchScope ls(c, "resolve_shadow", (uint64_t)nBand * (12 + 4 * (P.group ? P.peers.n : 1)));
+        if (nBand) k_resolve_shadow<<<(unsigned)((nBand + 255) / 256), 256, 0, st>>>(P, planes.p[FGL_PLANE_SHADOW], planes.p[FGL_PLANE_DEPTH]);
     }
     else
     {
         dim3 grid((P.W + 127) / 128, P.row1 - P.row0);
         if (P.passType == FGL_PASS_GEOMETRY)
         {
-            LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88 + (uint64_t)P.W * (P.H - (P.row1 - P.row0)) * 12);
-            k_resolve_geometry<<<dim3((P.W + 127) / 128, P.H), 128, 0, st>>>(P, planes);
+            const int rows = P.group ? P.row1 - P.row0 : P.H;  // stand-alone bands also resolve the depth of all other rows (SSAO)
+            LaunchScope ls(c, "resolve_geometry", (uint64_t)P.W * (P.row1 - P.row0) * 88 + (uint64_t)P.W * (rows - (P.row1 - P.row0)) * 12 +
+                                                      (P.group ? (uint64_t)P.W * (P.own1 - P.own0) * 4 * (P.peers.n - 1) : 0));
+            if (rows > 0) k_resolve_geometry<<<dim3((P.W + 127) / 128, rows), 128, 0, st>>>(P, planes);
         }
         else if (P.passType == FGL_PASS_FORWARD && forwardLight && P.row1 > P.row0)
         {

@@ -29,12 +29,16 @@
 
 #include "stream.h"
 
+#ifndef FGL_CHAIN_NW
+#define FGL_CHAIN_NW 2  // PCSS chain: 32-candidate words per row window (W = 32 * FGL_CHAIN_NW)
+#endif
+
 namespace
 {
 constexpr int    kMT = 624;
 constexpr int    kCB = 256;                      // generator blocks per checkpoint
 constexpr size_t kWindowCand = (size_t)64 << 20;  // candidates per build window
-constexpr int    kChainNW = 2;                   // PCSS chain: candidate offsets evaluated per row = 32 * kChainNW, centred on the prediction
+constexpr int    kChainNW = FGL_CHAIN_NW;                   // PCSS chain: candidate offsets evaluated per row = 32 * kChainNW, centred on the prediction
 
 __device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b)
 {
@@ -161,11 +165,29 @@ constexpr int kMMR = 128;   // V pass: output rows per CTA (32 columns); window 
 
 __device__ __forceinline__ float2 mm2(float2 a, float2 b) { return make_float2(fminf(a.x, b.x), fmaxf(a.y, b.y)); }
 
+// The box maps are only ever read at the texels the band's pixels map to (k_classify, k_pixel_masks, k_chunk_index), which
+// k_shadow_coords bounds by a texel rectangle (rect = x0, y0, x1, y1; x1 < x0: nobody reads).  Output tiles that cannot
+// intersect the rectangle grown by `margin` texels are skipped; rect == nullptr: the whole map.
+struct MapRegion
+{
+    const int* rect;
+    int        margin;
+};
+__device__ __forceinline__ bool region_skips(const MapRegion& g, int W, int H, int tx0, int tx1, int ty0, int ty1, int rowLo, int rowHi)
+{
+    if (!g.rect) return false;
+    const int x0 = __ldg(g.rect), y0 = __ldg(g.rect + 1), x1 = __ldg(g.rect + 2), y1 = __ldg(g.rect + 3);
+    if (x1 < x0 || y1 < y0) return true;
+    // rowLo / rowHi: extra rows the H pass has to provide for the V pass's window
+    return tx1 < x0 - g.margin || tx0 > x1 + g.margin || ty1 < y0 - g.margin + rowLo || ty0 > y1 + g.margin + rowHi;
+}
+
 template <bool FIRST>
-__global__ void __launch_bounds__(256) k_minmax_h(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
+__global__ void __launch_bounds__(256) k_minmax_h(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax, MapRegion region)
 {
     __shared__ float2 t[kMMW + 256];
     const int   y = blockIdx.y, x0 = blockIdx.x * kMMW, w = hi - lo + 1, nOut = min(kMMW, W - x0), n = nOut + w - 1;
+    if (region_skips(region, W, H, x0, x0 + nOut - 1, y, y, lo, hi)) return;
     const float inf = __int_as_float(0x7f800000);
     for (int e = threadIdx.x; e < n; e += 256)
     {
@@ -211,11 +233,12 @@ __global__ void __launch_bounds__(256) k_minmax_h(const float* imin, const float
 }
 
 // V pass: 32 columns x kMMR output rows per CTA, ping-pong tiles in dynamic shared memory (2 x (kMMR + w - 1) x 32 float2 <= 128 KB)
-__global__ void __launch_bounds__(512) k_minmax_v(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax)
+__global__ void __launch_bounds__(512) k_minmax_v(const float* imin, const float* imax, int W, int H, int lo, int hi, float* omin, float* omax, MapRegion region)
 {
     extern __shared__ __align__(16) unsigned char mmRaw[];
     const int   lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // 16 warps
     const int   x = blockIdx.x * 32 + lane, y0 = blockIdx.y * kMMR, w = hi - lo + 1, nOut = min(kMMR, H - y0), n = nOut + w - 1;
+    if (region_skips(region, W, H, blockIdx.x * 32, blockIdx.x * 32 + 31, y0, y0 + nOut - 1, 0, 0)) return;
     // two tiles of (kMMR + w - 1) rows x 32 columns (the launch sizes the allocation to the window, so two CTAs share an SM)
     float2(*t0)[32] = reinterpret_cast<float2(*)[32]>(mmRaw);
     float2(*t1)[32] = t0 + (kMMR + w - 1);
@@ -304,17 +327,48 @@ struct ChainPass
 
 // per pixel: shadow coordinate + bias (shadow.cpp:109-118) from the G-buffer (deferred lighting; forward mode
 // computes the same quantities per fragment in raster.cu)
-__global__ void __launch_bounds__(256) k_shadow_coords(ChainPass P, size_t first, size_t last, float4* sc4)
+// texel rectangle of the sites that can look at the box maps at all: the centre texel exactly as k_classify computes it
+struct TexelRect
 {
-    size_t n = (size_t)P.W * P.H, idx = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= last) return;
-    V3    pos = v3(P.worldpos[idx], P.worldpos[n + idx], P.worldpos[2 * n + idx]);
-    V3    nrm = v3(P.normal[idx], P.normal[n + idx], P.normal[2 * n + idx]);
-    V3    ln = v3(P.lndc[idx], P.lndc[n + idx], P.lndc[2 * n + idx]);
-    V3    lightDir = vnormalize(vsub(v3(P.lightPos[0], P.lightPos[1], P.lightPos[2]), pos));
-    V3    sc = vadd(vscale(ln, 0.5f), v3(0.5f, 0.5f, 0.5f));
-    float bias = fmaxf(P.biasSlope * (1.f - vdot(nrm, lightDir)), P.biasMin);
-    sc4[idx] = make_float4(sc.x, sc.y, sc.z, bias);
+    int x0, y0, x1, y1;
+};
+__device__ __forceinline__ void rect_add(const ChainPass& P, float scx, float scy, TexelRect& r)
+{
+    float ulo = scx + (-P.fsF), uhi = scx + P.fsF, vlo = scy + (-P.fsF), vhi = scy + P.fsF;
+    if (!(uhi < 0.f || ulo > 1.f || vhi < 0.f || vlo > 1.f) && ulo == ulo && vlo == vlo)
+    {
+        int cx = f2i_x86((float)P.sm.iw * clampf(scx, 0.f, 1.f)), cy = f2i_x86((float)P.sm.ih * clampf(scy, 0.f, 1.f));
+        r.x0 = min(r.x0, cx), r.x1 = max(r.x1, cx), r.y0 = min(r.y0, cy), r.y1 = max(r.y1, cy);
+    }
+}
+__global__ void k_rect_init(int* rect) { rect[0] = rect[1] = 0x7fffffff, rect[2] = rect[3] = -1; }
+
+// grid-stride: every thread keeps its rectangle in registers, a warp merges once at the end (four atomics per warp of the
+// whole launch — per-pixel atomics on four addresses would serialise in the L2)
+__global__ void __launch_bounds__(256) k_shadow_coords(ChainPass P, size_t first, size_t last, float4* sc4, int* rect)
+{
+    const size_t n = (size_t)P.W * P.H, stride = (size_t)gridDim.x * blockDim.x;
+    TexelRect    r;
+    r.x0 = r.y0 = 0x7fffffff, r.x1 = r.y1 = -1;
+    for (size_t idx = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < last; idx += stride)
+    {
+        V3    pos = v3(P.worldpos[idx], P.worldpos[n + idx], P.worldpos[2 * n + idx]);
+        V3    nrm = v3(P.normal[idx], P.normal[n + idx], P.normal[2 * n + idx]);
+        V3    ln = v3(P.lndc[idx], P.lndc[n + idx], P.lndc[2 * n + idx]);
+        V3    lightDir = vnormalize(vsub(v3(P.lightPos[0], P.lightPos[1], P.lightPos[2]), pos));
+        V3    sc = vadd(vscale(ln, 0.5f), v3(0.5f, 0.5f, 0.5f));
+        float bias = fmaxf(P.biasSlope * (1.f - vdot(nrm, lightDir)), P.biasMin);
+        sc4[idx] = make_float4(sc.x, sc.y, sc.z, bias);
+        if (rect) rect_add(P, sc.x, sc.y, r);
+    }
+    if (!rect) return;
+    r.x0 = __reduce_min_sync(0xffffffffu, r.x0), r.y0 = __reduce_min_sync(0xffffffffu, r.y0);
+    r.x1 = __reduce_max_sync(0xffffffffu, r.x1), r.y1 = __reduce_max_sync(0xffffffffu, r.y1);
+    if ((threadIdx.x & 31) == 0 && r.x1 >= r.x0)
+    {
+        atomicMin(rect, r.x0), atomicMin(rect + 1, r.y0);
+        atomicMax(rect + 2, r.x1), atomicMax(rect + 3, r.y1);
+    }
 }
 
 // blocker-search class of every site (a site = one consumer of the lighting-phase stream, in consumption order:
@@ -496,15 +550,23 @@ __device__ __forceinline__ uint32_t eval_pairs(const ChainRows& R, bool valid, i
     return w;
 }
 
-// pilot: every uncertain row at the crude offset "half of the uncertain rows before it have a blocker"
-__global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot)
+// pilot: every uncertain row at K crude offsets around "half of the uncertain rows before it have a blocker"; pilot[j] = how
+// many of the K chunks had a blocker.  The prediction of the chain is the prefix sum of pilot / K: the error of a K-sample
+// mean has the variance p (1 - p) / K per row, on top of the p (1 - p) of the row's own flag — the drift that ends a
+// super-chunk grows (1 + 1 / K) / 2 times as fast as with a single sample.
+__global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot, int K)
 {
     int  lane = threadIdx.x & 31;
     int  j = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = j < R.nU;
     size_t chunk = valid ? (size_t)R.base + R.Upix[j] + 2 * ((size_t)R.Uc1[j] + (size_t)(j >> 1)) : 0;
-    uint32_t w = eval_pairs(R, valid, j, chunk, lane);
-    if (valid) pilot[j] = (w >> lane) & 1u;
+    int    cnt = 0;
+    for (int q = 0; q < K; ++q)
+    {
+        uint32_t w = eval_pairs(R, valid, j, chunk + 2 * (size_t)q, lane);
+        cnt += (int)((w >> lane) & 1u);
+    }
+    if (valid) pilot[j] = cnt;
 }
 
 enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_ARRIVE = 4, CH_EPOCH = 5, CH_ERROR = 6, CH_ARRIVE_ROWS = 7, CH_NBLOCKERS = 8, CH_NFILTERED = 9 };
@@ -563,7 +625,8 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int k)
 }
 
 constexpr int kMaxGrid = 160;              // CTAs (= SMs) the tables are sized for; a B200 has 148
-constexpr int kMaxSpc = 3;                 // segments one CTA evaluates per iteration
+constexpr int kMaxSpc = 6;                 // segments one CTA evaluates per iteration (FGL_CHAIN_SEGS caps the iteration below grid * kMaxSpc)
+constexpr int kRowBatch = 3;               // rows a warp keeps in flight during the signature tests
 constexpr int kRowsCta = kMaxSpc * kSeg;  // rows of those segments
 
 // Shared memory of k_chain_fused (dynamic; CTA 0 also holds the tables of the whole iteration)
@@ -580,6 +643,7 @@ struct ChainSmem
     uint32_t           amb[kRowsCta * NW];  // candidates the signature test left undecided
     int                pre[kRowsCta * NW + 1];
     int                lo[kRowsCta];
+    uint16_t           queue[kRowsCta * W];  // work list of the undecided candidates: (word << 5) | bit
     uint4              pairQ[32][8];      // per warp: the eight candidates of the current step (chunk lo / hi, work-list word, bit)
     // composition (CTA 0)
     uint8_t G[kMaxSegs * W];
@@ -591,7 +655,7 @@ struct ChainSmem
 
 template <int NW>
 __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* state, const int* Ppre, uint8_t* G8all, uint32_t* GMall, int* segLoAll,
-                                                 uint32_t* rowBits, int* rowLo, uint8_t* flagU, int segsPerIter)
+                                                 uint32_t* rowBits, int* rowLo, uint8_t* flagU, int segsPerIter, int pilotK)
 {
     constexpr int W = 32 * NW;
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -633,17 +697,19 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
         const int mySegs = blockIdx.x < nSeg ? (nSeg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         constexpr int myWords = kRowsCta * NW;
 
-        // (1a) warp per row (up to kMaxSpc rows per warp, their loads in flight together): signature test of the W candidates
+        // (1a) warp per row (kMaxSpc rows per warp, kRowBatch of them in flight together): signature test of the W candidates
+        static_assert(kMaxSpc % kRowBatch == 0, "rows are processed in whole batches");
+        for (int ib = 0; ib < kMaxSpc; ib += kRowBatch)
         {
-            unsigned           upix[kMaxSpc], uc1[kMaxSpc];
-            unsigned long long F[kMaxSpc], E[kMaxSpc];
-            float4             sc[kMaxSpc];
-            int                lo[kMaxSpc], tt[kMaxSpc];
-            bool               rowValid[kMaxSpc];
+            unsigned           upix[kRowBatch], uc1[kRowBatch];
+            unsigned long long F[kRowBatch], E[kRowBatch];
+            float4             sc[kRowBatch];
+            int                lo[kRowBatch], tt[kRowBatch];
+            bool               rowValid[kRowBatch];
 #pragma unroll
-            for (int i = 0; i < kMaxSpc; ++i)
+            for (int i = 0; i < kRowBatch; ++i)
             {
-                tt[i] = (warp + 32 * i) * (int)gridDim.x + (int)blockIdx.x;
+                tt[i] = (warp + 32 * (ib + i)) * (int)gridDim.x + (int)blockIdx.x;
                 rowValid[i] = tt[i] < nLive;
                 upix[i] = uc1[i] = 0u, F[i] = E[i] = 0ull, sc[i] = make_float4(0.f, 0.f, 0.f, 0.f), lo[i] = 0;
                 if (rowValid[i])
@@ -653,12 +719,12 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
                     upix[i] = __ldg(R.Upix + j), uc1[i] = __ldg(R.Uc1 + j), F[i] = __ldg(R.UF + j), E[i] = __ldg(R.UE + j), sc[i] = __ldg(R.Usc + j);
                 }
             }
-            unsigned long long sg[kMaxSpc][NW];
-            size_t             chunk0[kMaxSpc];
+            unsigned long long sg[kRowBatch][NW];
+            size_t             chunk0[kRowBatch];
 #pragma unroll
-            for (int i = 0; i < kMaxSpc; ++i)
+            for (int i = 0; i < kRowBatch; ++i)
             {
-                lo[i] = rowValid[i] ? max(0, lo[i] - pre0 - W / 2) : 0;
+                lo[i] = rowValid[i] ? max(0, (lo[i] - pre0 + (pilotK >> 1)) / pilotK - W / 2) : 0;  // Ppre counts K samples per row
                 chunk0[i] = (size_t)R.base + 2 * kBefore + upix[i] + 2 * ((size_t)uc1[i] + m0 + (size_t)lo[i]);
 #pragma unroll
                 for (int h = 0; h < NW; ++h)
@@ -669,9 +735,9 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
                 }
             }
 #pragma unroll
-            for (int i = 0; i < kMaxSpc; ++i)
+            for (int i = 0; i < kRowBatch; ++i)
             {
-                const int rr = warp + 32 * i;
+                const int rr = warp + 32 * (ib + i);
 #pragma unroll
                 for (int h = 0; h < NW; ++h)
                 {
@@ -714,7 +780,15 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
             if (lane == 31) S.pre[myWords] = incl;
         }
         __syncthreads();
-        // (1c) the undecided candidates, eight per warp step.  Lanes 0..7 locate one candidate each (word of the work list,
+        // (1b') the work list itself: entry pre[w] + rank of bit b inside amb[w]  =  (w << 5) | b, written by the lane that owns
+        // the bit (warp per word) — the candidates are then addressed directly instead of searched for in the prefix array
+        for (int wi = warp; wi < myWords; wi += 32)
+        {
+            const uint32_t a = S.amb[wi];
+            if ((a >> lane) & 1u) S.queue[S.pre[wi] + __popc(a & ((1u << lane) - 1u))] = (uint16_t)((wi << 5) | lane);
+        }
+        __syncthreads();
+        // (1c) the undecided candidates, eight per warp step.  Lanes 0..7 take one candidate each off the work list (word,
         // bit inside the word, sample chunk).  Then, lane = tap: which of the candidate's 32 taps fall into a cell of E
         // (an undecided candidate has no sample in a cell of F; a tap outside E cannot block) — about 5 of 32.  Those taps
         // of all eight candidates are finally evaluated DENSELY, one tap per lane (the sample comes back from L1).
@@ -725,15 +799,9 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
                 const int nq = min(8, total - g0);
                 if (lane < nq)
                 {
-                    const int p = g0 + lane;
-                    int       loI = 0, hiI = myWords;  // pre[loI] <= p < pre[hiI]
-                    while (hiI - loI > 1)
-                    {
-                        int mid = (loI + hiI) >> 1;
-                        if (S.pre[mid] <= p) loI = mid;
-                        else hiI = mid;
-                    }
-                    const int                b = nth_set_bit(S.amb[loI], p - S.pre[loI]);
+                    const unsigned e = S.queue[g0 + lane];
+                    const int      loI = (int)(e >> 5);
+                    const int                b = (int)(e & 31u);
                     const unsigned long long chunk = S.rowChunk0[loI / NW] + 2ull * (unsigned)(32 * (loI % NW) + b);
                     S.pairQ[warp][lane] = make_uint4((unsigned)chunk, (unsigned)(chunk >> 32), (unsigned)loI, (unsigned)b);
                 }
@@ -961,9 +1029,9 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
 // latency-bound kernel leaves empty (DESIGN.md §4 "Overlap").
 #define FGL_CHAIN_KERNEL(NAME, ATTR)                                                                                                          \
     __global__ void ATTR NAME(ChainRows R, unsigned* state, const int* Ppre, uint8_t* G8all, uint32_t* GMall, int* segLoAll, uint32_t* rowBits, \
-                              int* rowLo, uint8_t* flagU, int segsPerIter)                                                                    \
+                              int* rowLo, uint8_t* flagU, int segsPerIter, int pilotK)                                                        \
     {                                                                                                                                         \
-        chain_fused_body<kChainNW>(R, state, Ppre, G8all, GMall, segLoAll, rowBits, rowLo, flagU, segsPerIter);                               \
+        chain_fused_body<kChainNW>(R, state, Ppre, G8all, GMall, segLoAll, rowBits, rowLo, flagU, segsPerIter, pilotK);                       \
     }
 FGL_CHAIN_KERNEL(k_chain_fused_r64, __launch_bounds__(1024, 1))
 FGL_CHAIN_KERNEL(k_chain_fused_r48, __maxnreg__(48))
@@ -1186,7 +1254,8 @@ struct SampleStream
     unsigned long long ssaoSamples = 0;
     // chain scratch
     DevBuf smTmpMin, smTmpMax, smMin, smMax, boxMin, boxMax, sc4, isU, isC1, posU, c1pre, Upix, Uc1, Usc, UF, UE, bits, flagU, hasB, kpre, chunkOf, mState;
-    DevBuf sig, vis, blockerList, pilot, Ppre, winLo, chainStats, rowBits;
+    DevBuf sig, vis, blockerList, pilot, Ppre, winLo, chainStats, rowBits, rect;
+    bool   rectValid = false;  // rect holds the texel rectangle of this frame's sites (deferred lighting); else the box maps cover the whole map
     unsigned long long sigChunks = 0;
     // device-side hand-off (peer mailboxes)
     DevBuf              mailbox, peerLocal;  // 16 x (epoch, value); {kDev, total, err}
@@ -1217,7 +1286,7 @@ void fgl_stream_destroy(fgl_ctx* c)
     if (s->mailbox.p) cudaFree(s->mailbox.p);
     if (s->peerLocal.p) cudaFree(s->peerLocal.p);
     DevBuf* all[] = { &s->ckpt, &s->window, &s->tileCounts, &s->tileOffsets, &s->counters, &s->ball, &s->disk, &s->smTmpMin, &s->smTmpMax, &s->smMin,
-                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->pilot, &s->Ppre, &s->winLo, &s->chainStats, &s->rowBits, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
+                      &s->smMax, &s->boxMin, &s->boxMax, &s->UF, &s->UE, &s->sig, &s->vis, &s->blockerList, &s->pilot, &s->Ppre, &s->winLo, &s->chainStats, &s->rowBits, &s->rect, &s->sc4, &s->isU, &s->isC1, &s->posU, &s->c1pre, &s->Upix, &s->Uc1, &s->Usc, &s->bits, &s->flagU, &s->hasB, &s->kpre,
                       &s->chunkOf, &s->mState };
     for (DevBuf* b : all)
         if (b->p) cudaFree(b->p);
@@ -1228,7 +1297,7 @@ void fgl_stream_destroy(fgl_ctx* c)
 void fgl_stream_begin_frame(fgl_ctx* c)
 {
     SampleStream* s = S_of(c);
-    s->prepValid = false, s->chainInFlight = false;
+    s->prepValid = false, s->chainInFlight = false, s->rectValid = false;
     if (s->peerOn) ++s->peerEpoch;
     s->ssaoThisFrame = false;
     s->ssaoSamples = 0;
@@ -1329,6 +1398,14 @@ int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S)
     return FGL_OK;
 }
 
+// |(float)(d * fs)| <= fsF for every |d| < 1: the largest tap offset of the blocker search as a float
+static float pcss_filter_bound(double fs)
+{
+    float fsF = (float)fs;
+    if (!((double)fsF >= fs)) fsF = nextafterf(fsF, 1e30f);
+    return fsF;
+}
+
 static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
 {
     size_t tmpBytes = 0;
@@ -1346,9 +1423,16 @@ static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
 //     plain launch, so that the other passes' blocks become resident next to it.  Co-residency then follows from one CTA per
 //     SM being placed first (highest stream priority, issued ahead of SSAO); should a CTA ever be kept waiting beyond the
 //     barriers' time-outs the kernel reports an error and the caller re-runs the chain exclusively (see the RESOLVE phase).
+// samples per row of the pilot (FGL_CHAIN_PILOT_K; the pilot kernel and the chain kernel must agree)
+static int chain_pilot_k()
+{
+    static const int k = getenv("FGL_CHAIN_PILOT_K") ? std::max(1, std::min(16, atoi(getenv("FGL_CHAIN_PILOT_K")))) : 4;
+    return k;
+}
+
 static int launch_chain(fgl_ctx* c, SampleStream* s, ChainRows& R, int nU, size_t n, int nC1, cudaStream_t st, bool shared)
 {
-    typedef void (*ChainKernel)(ChainRows, unsigned*, const int*, uint8_t*, uint32_t*, int*, uint32_t*, int*, uint8_t*, int);
+    typedef void (*ChainKernel)(ChainRows, unsigned*, const int*, uint8_t*, uint32_t*, int*, uint32_t*, int*, uint8_t*, int, int);
     static const int  segsEnv = getenv("FGL_CHAIN_SEGS") ? atoi(getenv("FGL_CHAIN_SEGS")) : 0;
     static const int  regsEnv = getenv("FGL_CHAIN_REGS") ? atoi(getenv("FGL_CHAIN_REGS")) : 0;
     static const int  coopEnv = getenv("FGL_CHAIN_COOP") ? atoi(getenv("FGL_CHAIN_COOP")) : -1;
@@ -1386,13 +1470,14 @@ static int launch_chain(fgl_ctx* c, SampleStream* s, ChainRows& R, int nU, size_
     if (int rc = fgl_reserve(c, s->rowBits, nRows * kChainNW * 4 + nRows * 4)) return rc;
     uint32_t*    rowBits = (uint32_t*)s->rowBits.p;
     int*         rowLo = (int*)(rowBits + nRows * kChainNW);
-    void*        args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter };
+    int          pilotK = chain_pilot_k();
+    void*        args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter, &pilotK };
     // algorithmic bytes: every uncertain row's record once (45 B) + every chunk signature of the band once (8 B)
     LaunchScope ls(c, "pcss_chain", (uint64_t)nU * 45 + ((uint64_t)n + 2ull * ((uint64_t)nC1 + (uint64_t)nU)) * 8);
     if (coop) FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(1024), args, smemBytes, st));
     else
     {
-        kernel<<<grid, 1024, smemBytes, st>>>(R, state, Ppre, G8, GM, segLo, rowBits, rowLo, flagU, segsPerIter);
+        kernel<<<grid, 1024, smemBytes, st>>>(R, state, Ppre, G8, GM, segLo, rowBits, rowLo, flagU, segsPerIter, pilotK);
         FGL_CUDA(c, cudaGetLastError());
     }
     s->chainWasShared = shared;
@@ -1480,8 +1565,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     if (int rc = fgl_reserve(c, s->mState, 64)) return rc;
     unsigned* chunkOfB = (unsigned*)s->chunkOf.p + siteLo;
 
-    float fsF = (float)L.pcssFilter;
-    if (!((double)fsF >= L.pcssFilter)) fsF = nextafterf(fsF, 1e30f);  // |(float)(d * fs)| <= fsF for |d| < 1
+    const float fsF = pcss_filter_bound(L.pcssFilter);
     int r = (int)ceil((double)L.sm.iw * (double)fsF) + 1;
     int bw = (int)ceil(0.25 * (double)L.sm.iw * (double)fsF) + 2;
     unsigned nb = (unsigned)((n + 255) / 256);
@@ -1502,8 +1586,10 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     {
     {
         LaunchScope ls(c, "pcss_minmax", smN * 48);
-        auto box = [&](int lo, int hi, float* omin, float* omax) -> int {
+        auto box = [&](int lo, int hi, float* omin, float* omax, int margin) -> int {
             const int w = hi - lo + 1;
+            MapRegion region;
+            region.rect = s->rectValid ? (const int*)s->rect.p : nullptr, region.margin = margin;
             float *   tmin = (float*)s->smTmpMin.p, *tmax = (float*)s->smTmpMax.p;
             if (w <= 129)
             {
@@ -1513,9 +1599,9 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
                     FGL_CUDA(c, cudaFuncSetAttribute(k_minmax_v, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 32 * 8));
                     attr = true;
                 }
-                k_minmax_h<true><<<dim3((L.sm.w + kMMW - 1) / kMMW, L.sm.h), 256, 0, st>>>(L.sm.d, nullptr, L.sm.w, L.sm.h, lo, hi, tmin, tmax);
+                k_minmax_h<true><<<dim3((L.sm.w + kMMW - 1) / kMMW, L.sm.h), 256, 0, st>>>(L.sm.d, nullptr, L.sm.w, L.sm.h, lo, hi, tmin, tmax, region);
                 k_minmax_v<<<dim3((L.sm.w + 31) / 32, (L.sm.h + kMMR - 1) / kMMR), 512, (size_t)2 * (kMMR + w - 1) * 32 * 8, st>>>(tmin, tmax, L.sm.w, L.sm.h, lo, hi, omin,
-                                                                                                                                  omax);
+                                                                                                                                  omax, region);
             }
             else
             {
@@ -1525,8 +1611,10 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
             }
             return FGL_OK;
         };
-        if (int rc = box(-r, r, (float*)s->smMin.p, (float*)s->smMax.p)) return rc;
-        if (int rc = box(0, bw - 1, (float*)s->boxMin.p, (float*)s->boxMax.p)) return rc;
+        // who reads where: k_classify / k_chunk_index at the centre texel and (deep-shadow shortcut) up to 3 r around it;
+        // k_pixel_masks at a cell's first texel, at most r from the centre
+        if (int rc = box(-r, r, (float*)s->smMin.p, (float*)s->smMax.p, 3 * r + 2)) return rc;
+        if (int rc = box(0, bw - 1, (float*)s->boxMin.p, (float*)s->boxMax.p, r + 2)) return rc;
         c->launches += 3;
     }
     P.smMin = (const float*)s->smMin.p, P.smMax = (const float*)s->smMax.p, P.r = r, P.fsF = fsF;
@@ -1577,7 +1665,7 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
         if (int rc = fgl_reserve(c, s->Ppre, (size_t)(nU + 1) * 4)) return rc;
         {
             LaunchScope ls(c, "pcss_chain_pilot", (uint64_t)nU * 48);
-            k_chain_pilot<<<(nU + 255) / 256, 256, 0, st>>>(R, (int*)s->pilot.p);
+            k_chain_pilot<<<(nU + 255) / 256, 256, 0, st>>>(R, (int*)s->pilot.p, chain_pilot_k());
         }
         FGL_CUDA(c, cudaMemsetAsync((int*)s->pilot.p + nU, 0, 4, st));
         if (int rc = scan_ints(c, (const int*)s->pilot.p, (int*)s->Ppre.p, (size_t)nU + 1)) return rc;
@@ -1702,10 +1790,20 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase)
     memcpy(P.lightPos, L.lightPos, 12);
     P.biasSlope = L.biasSlope, P.biasMin = L.biasMin, P.sm = L.sm;
     size_t lo = (size_t)L.row0 * L.W, hi = (size_t)L.row1 * L.W;
-    if (!((phase == FGL_VIS_RESOLVE || phase == FGL_VIS_LAUNCH) && s->prepValid))
+    if (!((phase == FGL_VIS_RESOLVE || phase == FGL_VIS_LAUNCH) && s->prepValid) && hi > lo)
     {
+        const bool pcss = L.shadowMode == FGL_SHADOW_PCSS;
+        static const bool noRect = getenv("FGL_NO_MAP_RECT") != nullptr;
+        s->rectValid = pcss && !noRect;
+        if (s->rectValid)
+        {
+            if (int rc = fgl_reserve(c, s->rect, 16)) return rc;
+            P.fsF = pcss_filter_bound(L.pcssFilter);
+            k_rect_init<<<1, 1, 0, c->stream>>>((int*)s->rect.p);
+        }
         LaunchScope ls(c, "shadow_coords", (hi - lo) * (36 + 16));
-        k_shadow_coords<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(P, lo, hi, (float4*)s->sc4.p);
+        const unsigned blocks = (unsigned)std::min<size_t>((hi - lo + 255) / 256, (size_t)c->numSMs * 16);
+        k_shadow_coords<<<blocks, 256, 0, c->stream>>>(P, lo, hi, (float4*)s->sc4.p, s->rectValid ? (int*)s->rect.p : nullptr);
     }
     // sort-first bands: the chain of this band starts from the number of blockers found in the bands before it
     return fgl_stream_site_visibility(c, L, n, (const float4*)s->sc4.p, lo, hi, c->chainBlockersBefore, phase);

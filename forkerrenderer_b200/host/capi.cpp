@@ -207,6 +207,35 @@ int frh_test_fragments(void* scenePtr, int shadow_mode, float* out, int max, int
     });
 }
 
+// ---- sort-first group: one frame on several GPUs (include/forkergl_b200.h "fgl_group_*", csrc/group.cu) ---------------------
+// One process per GPU.  The host side is these four calls; the processes only have to hand each other their 368-byte member
+// records once (any transport: bench.py uses torch.distributed's all_gather for that and for nothing else).
+//   frh_group_export(scene, member)            this process's record for the scene's frame size
+//   frh_group_connect(rank, world, members)    all records in rank order; then a barrier across the processes
+//   frh_render(scene, ...)                      every frame: this rank's band, everything else happens on the devices
+//   frh_group_read_frame(dst, bytes)            rank 0: the finished 8-bit frame
+int frh_group_member_bytes() { return (int)sizeof(FglGroupMember); }
+int frh_group_export(void* scene, void* member)
+{
+    return Guard([&] {
+        Scene* s = (Scene*)scene;
+        int    k = s->IsSSAAOn() ? s->GetSSAAKernelSize() : 1;
+        ForkerGL::Check(fgl_group_export(ForkerGL::Context(), s->GetWidth() * k, s->GetHeight() * k, (FglGroupMember*)member), "group export");
+    });
+}
+int frh_group_connect(int rank, int world, const void* members, int same_process)
+{
+    return Guard([&] { ForkerGL::Check(fgl_group_connect(ForkerGL::Context(), rank, world, (const FglGroupMember*)members, same_process), "group connect"); });
+}
+int frh_group_read_frame(void* dst, size_t bytes)
+{
+    return Guard([&] { ForkerGL::Check(fgl_group_read_frame(ForkerGL::Context(), dst, bytes), "group read frame"); });
+}
+int frh_group_disconnect()
+{
+    return Guard([&] { ForkerGL::Check(fgl_group_disconnect(ForkerGL::Context()), "group disconnect"); });
+}
+
 // Output::* of the reference's main (main.cpp:43-52) into `dir`.
 int frh_output_tga(const char* dir)
 {

@@ -134,36 +134,66 @@ def gather_bands(dist, torch, band_tensor, height, width, world):
 
 
 class Group:
-    """The sort-first group as bench.py drives it: one process per GPU, torch.distributed only for the rendezvous.
+    """The sort-first group as bench.py drives it: one process per GPU; torch.distributed is only the rendezvous.
 
-    mode 'nccl': every GPU rasterises the whole shadow map, renders its band, the PCSS chain state travels through peer
-    mailboxes (or NCCL send / recv when IPC is unavailable) and the RGB8 bands are all-gathered with NCCL."""
+    mode 'peer' (default): the C++ group of include/forkergl_b200.h (fgl_group_*, csrc/group.cu).  The processes exchange
+    their member records once (all_gather_object); from then on every frame is `frh_render` on each rank: band-split shadow
+    pass and camera passes, shadow map / depth rows / finished 8-bit rows / PCSS chain state stored into the peers' memory
+    by the producing kernels, ordered by device-side epoch flags.  Rank 0 reads the frame with frh_group_read_frame.
 
-    def __init__(self, fgl, dist, rank, world, renderer, mode="nccl"):
+    mode 'nccl' (the round-1 path, kept for comparison): every GPU rasterises the whole shadow map and the whole depth
+    plane, renders its band, the chain state travels through peer mailboxes (or NCCL send / recv) and the RGB8 bands are
+    all-gathered with NCCL."""
+
+    def __init__(self, fgl, dist, rank, world, renderer, mode="peer"):
         import torch
         self.torch, self.fgl, self.dist, self.rank, self.world, self.r, self.mode = torch, fgl, dist, rank, world, renderer, mode
-        self.device = torch.device("cuda", torch.cuda.current_device())
         H, W = renderer.height, renderer.width
         self.r0, self.r1, self.per = band_rows(H, world, rank)
+        self.host_read_bytes = 0
+        if mode == "peer":
+            host, scene = renderer.host, renderer.scene
+            if not scene.deferred or scene.ssaa:
+                raise RuntimeError("a sort-first group renders deferred frames without SSAA")
+            mine = host.group_export(scene)
+            members = [None] * world
+            dist.all_gather_object(members, mine)
+            host.group_connect(rank, world, members)
+            dist.barrier()  # every context is connected before any of them begins a frame
+            return
+        self.device = torch.device("cuda", torch.cuda.current_device())
         self.comm = TorchComm(dist, self.device)
         self.peer = bool(renderer.pcss and setup_peer_handoff(fgl, dist, rank, world, H))
         self.band = torch.empty((self.per, W, 3), dtype=torch.uint8, device=self.device)
         self.full = None
         self.host_frame = None
-        self.host_read_bytes = 0
 
     def describe(self):
+        if self.mode == "peer":
+            return ("sort-first row bands, %d rows per GPU; shadow pass and camera passes band-split (per-triangle set-up culls to the band), shadow map rows / "
+                    "depth rows / RGB8 rows / PCSS chain state stored into the peers' memory over NVLink by the producing kernels, device-side epoch flags, "
+                    "no NCCL on the data path" % self.per)
         return ("sort-first row bands, %d rows per GPU, geometry and shadow pass replicated, RGB8 bands all-gathered with NCCL, PCSS chain state "
                 "handed on through %s" % (self.per, "peer memory (device-side wait)" if self.peer else "the host (NCCL send/recv)"))
 
     def render_frame(self, gather=True):
+        if self.mode == "peer":
+            self.r.host.render(self.r.scene, self.r.shadow_mode, self.r.materialize)
+            return None
         render_frame(self.r, self.rank, self.world, self.comm, band_out=(self.band.data_ptr(), self.band.numel()), peer=self.peer)
         if gather:
             self.full = gather_bands(self.dist, self.torch, self.band, self.r.height, self.r.width, self.world)
         return self.full
 
     def read_frame(self):
-        """Rank 0: the gathered frame in page-locked host memory (numpy view); other ranks: waits for their stream."""
+        """Rank 0: the finished frame in page-locked host memory (numpy); other ranks: waits for their stream."""
+        if self.mode == "peer":
+            if self.rank != 0:
+                self.fgl.sync()
+                return None
+            img = self.r.host.group_read_frame(self.r.height, self.r.width)
+            self.host_read_bytes = 0  # counted by the library (fgl_transfer_bytes)
+            return img
         stream = self.torch.cuda.current_stream()
         if self.rank != 0:
             stream.synchronize()
@@ -176,4 +206,7 @@ class Group:
         return self.host_frame.numpy()
 
     def close(self):
-        pass
+        if self.mode == "peer":
+            self.fgl.sync()
+            self.dist.barrier()
+            self.r.host.group_disconnect()

@@ -194,6 +194,32 @@ int fgl_chain_peer_connect(fgl_ctx* ctx, void* next_device_ptr, const void* next
 int fgl_set_chain_blockers_before(fgl_ctx* ctx, uint64_t blockers);
 int fgl_get_chain_blockers(fgl_ctx* ctx, uint64_t* out_blockers);
 
+/* ---- sort-first group: one frame on several GPUs of one NVLink / NVSwitch box ------------------------------------------
+ * One context per GPU (usually one process per GPU).  Context r renders row band r of the screen and of the shadow map and
+ * its kernels store what the other bands need straight into the other contexts' planes over NVLink: the shadow map rows
+ * (ShadowBuffer of every context), the camera depth rows (DepthBuffer of every context; SSAO gathers depth anywhere), the
+ * finished 8-bit rows (rank 0's frame) and the PCSS chain's running blocker count (the next band's mailbox).  Ordering is
+ * kept on the device by epoch flags; the host only exchanges the FglGroupMember records once (csrc/group.cu).
+ *   fgl_group_export   sizes this context's exchanged planes for a width x height frame and describes them: CUDA IPC
+ *                      handles (other processes) and raw device pointers (contexts of the same process)
+ *   fgl_group_connect  members[0..world) = the records of all contexts in rank order (this context's own at [rank]).
+ *                      EVERY context must have returned from fgl_group_connect before any of them begins a frame.
+ *                      From then on Render::Render (or the raw pass calls) on this context renders its band; all contexts
+ *                      must render the same sequence of frames.  Deferred mode only; SSAA is not available in a group.
+ *   fgl_group_read_frame  rank 0: waits (on the device) for every band of the current frame, then copies the 8-bit frame
+ *                      (FGL_PLANE_FRAME_RGB8 layout) to host memory; other ranks: FGL_ERR_STATE
+ *   fgl_group_disconnect  back to a stand-alone context */
+typedef struct FglGroupMember
+{
+    unsigned char shadow_ipc[64], depth_ipc[64], frame_ipc[64], flags_ipc[64], chain_ipc[64];
+    void *        shadow_ptr, *depth_ptr, *frame_ptr, *flags_ptr, *chain_ptr;
+    int           width, height, device, reserved;
+} FglGroupMember;
+int fgl_group_export(fgl_ctx* ctx, int width, int height, FglGroupMember* out_member);
+int fgl_group_connect(fgl_ctx* ctx, int rank, int world, const FglGroupMember* members, int same_process);
+int fgl_group_read_frame(fgl_ctx* ctx, void* dst_host, size_t dst_bytes);
+int fgl_group_disconnect(fgl_ctx* ctx);
+
 /* ---- draw submission ------------------------------------------------------------------------------- */
 /* Mesh::Draw (src/mesh.cpp:10-25) for every face of the mesh: vertex program x3 + ForkerGL::DrawTriangle
  * (src/forkergl.cpp:239-324).  Primitive ids follow submission order.  The triangles are rasterised when the

@@ -1148,6 +1148,10 @@ int fgl_enable_timing(fgl_ctx*, int) { return FGL_OK; }
 int fgl_reset_timings(fgl_ctx*) { return FGL_OK; }
 int fgl_get_timings(fgl_ctx*, FglTiming*, int, int* n) { if (n) *n = 0; return FGL_OK; }
 int fgl_launch_count(fgl_ctx*, uint64_t* o) { if (o) *o = 0; return FGL_OK; }
+int fgl_group_export(fgl_ctx* c, int, int, FglGroupMember*) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle renders whole frames"); }
+int fgl_group_connect(fgl_ctx* c, int, int, const FglGroupMember*, int) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle renders whole frames"); }
+int fgl_group_read_frame(fgl_ctx* c, void*, size_t) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle renders whole frames"); }
+int fgl_group_disconnect(fgl_ctx*) { return FGL_OK; }
 int fgl_transfer_bytes(fgl_ctx*, uint64_t* a, uint64_t* b) { if (a) *a = 0; if (b) *b = 0; return FGL_OK; }
 int fgl_prepare_screen_space_pixels(fgl_ctx*, const float*, const float*, const float*, int) { return FGL_OK; }  // nothing to split on one CPU
 int fgl_chain_peer_mailbox(fgl_ctx* c, void**, void*, size_t) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle has no peer memory"); }
