@@ -203,7 +203,7 @@ struct fgl_ctx
     std::vector<DrawCmdD> draws;
     int                   primCounter = 0;  // submission index of the next triangle in this pass
     int                   flushedPrims = 0;
-    DevBuf                drawsDev, setup, vary, zndc, nblk, blkScan, scanTmp;
+    DevBuf                drawsDev, setup, vary, zndc, nblk, blkScan, scanTmp, tileState;
     DevBuf                fragCount, fragOffset, frags, nPass, passOff, siteOfPixel, siteKeys, siteVals, siteSc4, sortTmp;
     std::vector<DevBuf>   preChunks;  // device copies of fgl_draw_triangles arrays, alive until the pass ends
     size_t                preUsed = 0;

@@ -60,12 +60,20 @@ __device__ __forceinline__ SetupRegs load_setup(const TriSetup* s, int prim)
 }
 
 // -------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int smallArea)
+// The work items of k_raster_blocks (32 x 32 blocks of the large triangles' bounding boxes) are numbered by a two-level
+// exclusive scan of the per-triangle block counts: inside k_setup every CTA (a tile of kSetupTile triangles) scans its own
+// counts (blkScan[i] = blocks of the tile's triangles in front of triangle i) and stores its sum; k_tile_scan then scans the
+// tile sums (one small CTA: a 10 M-triangle pass has 78 k tiles).  item -> (tile, triangle) is two short binary searches.
+constexpr int kSetupTile = 128;
+
+__global__ void __launch_bounds__(kSetupTile) k_setup(RasterPass P, int primBegin, int smallArea, int* tileBase)
 {
-    int prim = primBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (prim >= P.nPrims) return;
-    const DrawCmdD& d = find_draw(P.draws, P.nDraws, prim);
-    int             face = prim - d.firstPrim;
+    __shared__ int sWarpSum[kSetupTile / 32];
+    const int  tile = blockIdx.x;
+    const int  prim = primBegin + tile * kSetupTile + (int)threadIdx.x;
+    const bool live = prim < P.nPrims;
+    const DrawCmdD& d = find_draw(P.draws, P.nDraws, live ? prim : P.nPrims - 1);
+    int             face = (live ? prim : P.nPrims - 1) - d.firstPrim;
     bool            shadowPass = P.passType == FGL_PASS_SHADOW;
 
     // ---- positions first: clip space, viewport, integer snap, bounding box (forkergl.cpp:241-255) — enough to decide whether
@@ -141,6 +149,29 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
         }
         if (sane) flags |= 8;
     }
+    if (!live) nb = 0;
+    {   // blkScan[i] = blocks of the tile's triangles in front of triangle primBegin + i; tileBase[tile] = blocks of the tile
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int       incl = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) sWarpSum[wid] = incl;
+        __syncthreads();
+        int excl = incl - nb, sum = 0;
+#pragma unroll
+        for (int w = 0; w < kSetupTile / 32; ++w)
+        {
+            if (w < wid) excl += sWarpSum[w];
+            sum += sWarpSum[w];
+        }
+        if (live) P.blkScan[prim - primBegin] = excl;  // tile-local
+        if (threadIdx.x == 0) tileBase[tile] = sum;
+    }
+    if (!live) return;
     P.nblk[prim] = nb;
     int4* so = reinterpret_cast<int4*>(P.setup + prim);
     if (flags & TRI_SKIP)
@@ -195,42 +226,77 @@ __global__ void __launch_bounds__(128) k_setup(RasterPass P, int primBegin, int 
     for (int i = 0; i < 12; ++i) vo[i] = make_float4(vy.f[4 * i], vy.f[4 * i + 1], vy.f[4 * i + 2], vy.f[4 * i + 3]);
 }
 
-// Exclusive scan of up to a few hundred thousand ints by one CTA (the two-kernel device-wide scan costs more in
-// launch latency than the work is worth for the meshes of the reference's scenes).
-struct ScanCarry
+// the tile-local half of the scan for counts that already exist (all triangles of a pass that was flushed in pieces)
+__global__ void __launch_bounds__(kSetupTile) k_tile_local_scan(const int* nblk, int* blkScan, int* tileBase, int n)
 {
-    int running;
-    __device__ int operator()(int blockAggregate)
-    {
-        int old = running;
-        running += blockAggregate;
-        return old;
-    }
-};
-__global__ void __launch_bounds__(1024) k_scan_small(const int* in, int* out, int n)
-{
-    typedef cub::BlockScan<int, 1024> Scan;
-    __shared__ typename Scan::TempStorage tmp;
-    ScanCarry carry;
-    carry.running = 0;
-    for (int base = 0; base < n; base += 4096)
-    {
-        int v[4], r[4];
+    __shared__ int sWarpSum[kSetupTile / 32];
+    const int i = blockIdx.x * kSetupTile + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nb = i < n ? nblk[i] : 0;
+    int       incl = nb;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) sWarpSum[wid] = incl;
+    __syncthreads();
+    int excl = incl - nb, sum = 0;
+#pragma unroll
+    for (int w = 0; w < kSetupTile / 32; ++w)
+    {
+        if (w < wid) excl += sWarpSum[w];
+        sum += sWarpSum[w];
+    }
+    if (i < n) blkScan[i] = excl;
+    if (threadIdx.x == 0) tileBase[blockIdx.x] = sum;
+}
+
+// in-place exclusive scan of the nTiles tile sums, total behind them: one CTA walks the array in coalesced chunks of 4096
+// (four consecutive values per thread), carrying the running sum
+__global__ void __launch_bounds__(1024) k_tile_scan(int* tileBase, int nTiles)
+{
+    __shared__ int sWarp[32], sCarry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    for (int base = 0; base < nTiles; base += 4096)
+    {
+        const int i0 = base + 4 * (int)threadIdx.x;
+        int       v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = i0 + k < nTiles ? tileBase[i0 + k] : 0;
+        const int sum = v[0] + v[1] + v[2] + v[3];
+        int       incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
         {
-            int i = base + threadIdx.x * 4 + k;
-            v[k] = i < n ? in[i] : 0;
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        Scan(tmp).ExclusiveSum(v, r, carry);
+        if (lane == 31) sWarp[wid] = incl;
         __syncthreads();
+        const int carry = sCarry;
+        int       before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w)
+        {
+            const int ws = sWarp[w];
+            if (w < wid) before += ws;
+            all += ws;
+        }
+        int run = carry + before + incl - sum;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
         {
-            int i = base + threadIdx.x * 4 + k;
-            if (i < n) out[i] = r[k];
+            if (i0 + k < nTiles) tileBase[i0 + k] = run;
+            run += v[k];
         }
+        __syncthreads();
+        if (threadIdx.x == 0) sCarry = carry + all;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) tileBase[nTiles] = sCarry;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -310,27 +376,38 @@ __global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegi
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBegin, int nNew)
+__global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBegin, int nNew, const int* tileBase)
 {
     const int lane = threadIdx.x & 31;
     const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    const int total = P.blkScan[nNew];  // blkScan = exclusive scan over the nNew triangles of this flush (+ total)
+    const int nTiles = (nNew + kSetupTile - 1) / kSetupTile;
+    const int total = tileBase[nTiles];
     int       cachedTri = -1, cachedBegin = 0, cachedEnd = 0;
     SetupRegs s;
     TriCover  tc;
     for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warpsPerGrid)
     {
         if (item < cachedBegin || item >= cachedEnd)
-        {   // upper_bound over the exclusive scan: last triangle whose first block index is <= item
-            int lo = 0, hi = nNew - 1;
+        {   // last tile whose first item is <= item, then the last triangle of that tile whose first item is <= item
+            int lo = 0, hi = nTiles - 1;
             while (lo < hi)
             {
                 int mid = (lo + hi + 1) >> 1;
-                if (__ldg(P.blkScan + mid) <= item) lo = mid;
+                if (__ldg(tileBase + mid) <= item) lo = mid;
                 else hi = mid - 1;
             }
-            cachedTri = primBegin + lo;
-            cachedBegin = __ldg(P.blkScan + lo), cachedEnd = __ldg(P.blkScan + lo + 1);
+            const int tile = lo, base = __ldg(tileBase + tile), t0 = tile * kSetupTile, rel = item - base;
+            lo = 0, hi = min(kSetupTile, nNew - t0) - 1;
+            while (lo < hi)
+            {
+                int mid = (lo + hi + 1) >> 1;
+                if (__ldg(P.blkScan + t0 + mid) <= rel) lo = mid;
+                else hi = mid - 1;
+            }
+            const int i = t0 + lo;
+            cachedTri = primBegin + i;
+            cachedBegin = base + __ldg(P.blkScan + i);
+            cachedEnd = cachedBegin + __ldg(P.nblk + cachedTri);
             s = load_setup(P.setup, cachedTri);
             tc = make_cover(s.X[0], s.Y[0], s.X[1], s.Y[1], s.X[2], s.Y[2]);
         }
@@ -665,24 +742,25 @@ int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t*
     // block work items over ALL triangles of the pass (the depth raster may have been flushed in pieces)
     if (int rc = fgl_reserve(c, c->blkScan, ((size_t)nPrims + 1) * 4)) return rc;
     P.blkScan = (int*)c->blkScan.p;
+    const int nTiles = (nPrims + kSetupTile - 1) / kSetupTile;
+    if (int rc = fgl_reserve(c, c->tileState, ((size_t)nTiles + 1) * 4)) return rc;
+    int* tileBase = (int*)c->tileState.p;
+    k_tile_local_scan<<<nTiles, kSetupTile, 0, st>>>(P.nblk, P.blkScan, tileBase, nPrims);
+    k_tile_scan<<<1, 1024, 0, st>>>(tileBase, nTiles);
     size_t tmpBytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, P.nblk, P.blkScan, nPrims + 1, st);
-    size_t tmp2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, (unsigned*)nullptr, (unsigned*)nullptr, (int)nPix + 1, st);
-    tmpBytes = std::max(tmpBytes, tmp2);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, (unsigned*)nullptr, (unsigned*)nullptr, (int)nPix + 1, st);
     if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
-    cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, P.nblk, P.blkScan, nPrims + 1, st);
     auto raster = [&](int mode) {
         LaunchScope ls(c, mode == RM_COUNT ? "forward_frag_count" : "forward_frag_fill", 0);
         if (mode == RM_COUNT)
         {
             k_raster_small<RM_COUNT><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
-            k_raster_blocks<RM_COUNT><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims);
+            k_raster_blocks<RM_COUNT><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims, tileBase);
         }
         else
         {
             k_raster_small<RM_FILL><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
-            k_raster_blocks<RM_FILL><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims);
+            k_raster_blocks<RM_FILL><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims, tileBase);
         }
         ++c->launches;
     };
@@ -756,29 +834,22 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
     int          primBegin = c->flushedPrims;
     int          nNew = P.nPrims - primBegin;
     size_t       nPix = (size_t)P.W * P.H;
+    int*         tileBase = nullptr;
     // Thread-per-triangle only pays off when there are enough small triangles to fill the machine; otherwise every
     // triangle takes the warp-per-block path (a small triangle is a single block).
     const int smallArea = nNew >= 65536 ? kSmallArea : 0;
     if (nNew > 0)
     {
+        const int nTiles = (nNew + kSetupTile - 1) / kSetupTile;
+        if (int rc = fgl_reserve(c, c->tileState, ((size_t)nTiles + 1) * 4)) return rc;
+        tileBase = (int*)c->tileState.p;
         {
             LaunchScope ls(c, "setup", (uint64_t)nNew * 320);
-            k_setup<<<(nNew + 127) / 128, 128, 0, st>>>(P, primBegin, smallArea);
+            k_setup<<<nTiles, kSetupTile, 0, st>>>(P, primBegin, smallArea, tileBase);
         }
-        // exclusive scan of the block counts of the new triangles -> blkScan[primBegin .. nPrims]
-        if (nNew < 200000)
         {
-            LaunchScope ls(c, "scan", (uint64_t)nNew * 8);
-            k_scan_small<<<1, 1024, 0, st>>>(P.nblk + primBegin, P.blkScan, nNew + 1);
-        }
-        else
-        {
-            size_t tmpBytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
-            if (int rc = fgl_reserve(c, c->scanTmp, tmpBytes)) return rc;
-            LaunchScope ls(c, "scan", (uint64_t)nNew * 8);
-            // the scan runs over nNew + 1 inputs so that entry nNew holds the total (nblk has one spare, zeroed, slot)
-            cub::DeviceScan::ExclusiveSum(c->scanTmp.p, tmpBytes, P.nblk + primBegin, P.blkScan, nNew + 1, st);
+            LaunchScope ls(c, "scan", (uint64_t)nTiles * 8);
+            k_tile_scan<<<1, 1024, 0, st>>>(tileBase, nTiles);
         }
         if (smallArea > 0)
         {
@@ -787,7 +858,7 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
         }
         {
             LaunchScope ls(c, "raster_blocks", 0);
-            k_raster_blocks<RM_DEPTH><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew);
+            k_raster_blocks<RM_DEPTH><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew, tileBase);
         }
     }
     // sort-first group: the resolves store into the other contexts' planes — not before those have begun this frame
