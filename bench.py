@@ -43,6 +43,8 @@ WORKLOADS = {
     "c2": ("scenes/c2.scene", "pcf", 0, 0, "scenes/c2.scene: plane + african_head, 1920x1080 forward Blinn-Phong + normal/specular maps, PCF"),
     "c4": ("scenes/c4_catbox.scene", "hard", 1, 1, "scenes/c4_catbox.scene: SSAA 2x (2560x1600 raster), Repeat + Linear textures"),
     "c5": ("@c5", "pcss", 1, 1, "C5: generated 2237x2237-quad height field OBJ (10 008 338 triangles) + plane, deferred PBR, PCSS + SSAO, Repeat + Linear, 7680x4320"),
+    "c5_hard": ("@c5", "hard", 1, 1, "C5 geometry with the hard-shadow filter (no sample-stream chain): generated 10 008 338-triangle OBJ + plane, deferred PBR, hard shadows + SSAO, 7680x4320"),
+    "c5_pcf": ("@c5", "pcf", 1, 1, "C5 geometry with the PCF filter (closed-form sample offsets, no chain): generated 10 008 338-triangle OBJ + plane, deferred PBR, PCF + SSAO, 7680x4320"),
     "c5_small": ("@c5_small", "pcss", 1, 1, "C5 reduced: generated 700x700-quad height field OBJ (980 000 triangles) + plane, deferred PBR, PCSS + SSAO, 1920x1080"),
 }
 ASSETS = os.path.join(REPO, "oracle", "_ref", "assets")
@@ -199,18 +201,18 @@ def run_reference_arm(args):
     return 0
 
 
-def make_renderer(args, local, world, dist):
+def make_renderer(args, local, world, dist, instance=0):
     from forkerrenderer_b200 import binding as B
     from forkerrenderer_b200 import multigpu as M
     scene_file, shadow, wrap, filt, desc = WORKLOADS[args.workload]
-    if scene_file.startswith("@"):
+    if scene_file.startswith("@") and instance == 0:
         # generated once per box: local rank 0 writes the files, the others wait for them
         if local == 0:
             scene_of(args.workload)
         if dist is not None:
             dist.barrier()
     path, assets, _, _ = scene_of(args.workload)
-    host = B.product_host()
+    host = B.product_host(instance)
     t0 = time.perf_counter()
     sc = host.load_scene(path, assets, wrap, filt)
     r = M.FacadeRenderer(host, sc, shadow, materialize=False)
@@ -240,10 +242,87 @@ def ncu_counters(workload, kernel):
     return out or None
 
 
+class Instance:
+    """One frame in flight: its own facade instance (scene, fgl context, group membership), CUDA stream and host thread."""
+
+    def __init__(self, args, local, world, rank, dist, index, torch, M):
+        self.r, self.info = make_renderer(args, local, world, dist, instance=index)
+        self.fgl, self.torch, self.world, self.rank = self.r.fgl, torch, world, rank
+        self.stream = torch.cuda.Stream()
+        self.fgl.set_stream(self.stream.cuda_stream)
+        self.group = M.Group(self.fgl, dist, rank, world, self.r, mode=args.group) if world > 1 else None
+        self.image = None
+
+    def frame(self, gather=True):
+        """One frame; with several GPUs: this rank's band (chain hand-off and gather of the 8-bit rows happen on the devices)."""
+        with self.torch.cuda.stream(self.stream):
+            if self.world > 1:
+                return self.group.render_frame(gather=gather)
+            self.r.begin((0, -1))
+            self.r.finish()
+        return None
+
+    def read(self):
+        """The finished 8-bit frame in page-locked host memory (rank 0 of a group; other ranks wait for their stream)."""
+        with self.torch.cuda.stream(self.stream):
+            if self.world > 1:
+                self.image = self.group.read_frame()
+            else:
+                self.image = self.fgl.read_plane("ssaa_u8" if self.info["ssaa"] else "frame_u8", pinned=True)
+        return self.image
+
+    def sync(self):
+        self.fgl.sync()
+        self.stream.synchronize()
+
+
+def run_frames(insts, count, read, torch):
+    """Renders `count` frames, frame i on instance i % len(insts), every instance driven by its own host thread (the frame
+    call blocks in the two host read-backs of a PCSS frame, so one thread could not keep two frames in flight).
+    Returns (device ms from the start to the last instance's end, CUDA events; wall-clock seconds)."""
+    n = len(insts)
+    for it in insts:
+        it.sync()
+    torch.cuda.synchronize()
+    start = torch.cuda.Event(enable_timing=True)
+    start.record(insts[0].stream)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in insts]
+    errors = []
+    device = torch.cuda.current_device()
+
+    def work(k):
+        try:
+            torch.cuda.set_device(device)  # the current device is per thread
+            it = insts[k]
+            for _ in range(k, count, n):
+                it.frame()
+                if read:
+                    it.read()
+            ends[k].record(it.stream)
+        except Exception as e:  # surfaced by the caller
+            errors.append(e)
+
+    t0 = time.perf_counter()
+    if n == 1:
+        work(0)
+    else:
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    for it in insts:
+        it.sync()
+    wall = time.perf_counter() - t0
+    return max(start.elapsed_time(e) for e in ends[: min(n, count)]), wall
+
+
 def run_ours(args):
     import numpy as np
     import torch
-    from forkerrenderer_b200 import binding as B
+    from forkerrenderer_b200 import binding as B  # noqa: F401
     from forkerrenderer_b200 import multigpu as M
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,100 +339,110 @@ def run_ours(args):
     torch.cuda.set_device(local)
     os.environ["FGL_DEVICE"] = str(local)
 
-    _dbg("process group up, building the renderer")
-    r, info = make_renderer(args, local, world, dist)
-    fgl = r.fgl
-    W, H = r.width, r.height            # raster size (output size x SSAA factor)
+    # L2: a frame streams its planes (100 B / pixel) and, with SSAO / a stochastic shadow filter, its sample tables (384 B / pixel
+    # of ball samples, >= 512 B / pixel of disk samples).  Where that is far beyond the 126 MB L2 nothing needs flushing; small
+    # workloads get an explicit flush between frames and therefore render one frame at a time.
+    scene_txt = "" if WORKLOADS[args.workload][0].startswith("@") else open(os.path.join(REPO, WORKLOADS[args.workload][0])).read()
+    cfgd = config_of(args.workload, world)
+    ssao_on = WORKLOADS[args.workload][0].startswith("@") or re.search(r"^ssao\s+on", scene_txt, re.M) is not None
+    per_px = 100 + (384 if ssao_on else 0) + (512 if WORKLOADS[args.workload][1] in ("pcf", "pcss") else 0)
+    k2 = 4 if re.search(r"^ssaa\s+on", scene_txt, re.M) else 1
+    stream_bytes = cfgd["width"] * cfgd["height"] * k2 * per_px // world
+    small = stream_bytes < (512 << 20)
+    # default: two frames in flight on one GPU (the latency-bound PCSS chain of one frame runs next to the other frame's passes);
+    # in a group the chain's serial relay through the bands bounds the frame, a second frame in flight buys nothing (profiles/)
+    want = args.inflight if args.inflight > 0 else (2 if world == 1 else 1)
+    inflight = 1 if (small or (world > 1 and args.group != "peer")) else want
+
+    _dbg("process group up, building %d renderer instance(s)" % inflight)
+    insts = [Instance(args, local, world, rank, dist, k, torch, M) for k in range(inflight)]
+    first = insts[0]
+    fgl, info, group = first.fgl, first.info, first.group
+    W, H = first.r.width, first.r.height            # raster size (output size x SSAA factor)
     out_px = info["out_w"] * info["out_h"]
-    stream = torch.cuda.Stream()
-    fgl.set_stream(stream.cuda_stream)
-    group = M.Group(fgl, dist, rank, world, r, mode=args.group) if world > 1 else None
     _dbg("group mode: %s" % (group.describe() if group else "single GPU"))
 
     def barrier():
-        fgl.sync()
+        for it in insts:
+            it.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # L2 flush between timed iterations for workloads whose planes could sit in the 126 MB L2
-    plane_bytes = W * H * 100 // world
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if plane_bytes < (512 << 20) else None
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
 
     def flush_l2():
         if flush_buf is not None:
             flush_buf.fill_(1)
             torch.cuda.synchronize()
 
-    def frame(gather=True):
-        """One frame; with several GPUs: this rank's band, the chain hand-off, and the gather of the 8-bit bands on rank 0."""
-        with torch.cuda.stream(stream):
-            if world > 1:
-                return group.render_frame(gather=gather)
-            r.begin((0, -1))
-            r.finish()
-        return None
-
     for _ in range(args.warmup):
-        frame()
+        for it in insts:
+            it.frame()
     barrier()
     _dbg("warm-up done")
 
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    l0 = fgl.launch_count()
-    ev = []
-    for _ in range(args.steps):
-        flush_l2()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        frame()
-        e1.record(stream)
-        ev.append((e0, e1))
+    l0 = sum(it.fgl.launch_count() for it in insts)
+    if flush_buf is None:
+        ms_total, _ = run_frames(insts, args.steps, False, torch)
+        ms = ms_total / args.steps
+    else:  # one frame at a time, L2 flushed in between
+        ev = []
+        for _ in range(args.steps):
+            flush_l2()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(first.stream)
+            first.frame()
+            e1.record(first.stream)
+            ev.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
     barrier()
-    launches = fgl.launch_count() - l0
-    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    launches = sum(it.fgl.launch_count() for it in insts) - l0
 
     # ---- end to end: facade call(s) + the finished 8-bit frame in host memory, wall clock --------------------------
-    e2e_t = []
     frame_hash = None
-    E2E_WARM = 2  # untimed passes: the first one allocates the page-locked frame buffer and fingerprints the frame
-    h2d0 = d2h0 = 0
-    for i in range(args.steps + E2E_WARM):
-        flush_l2()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-        if i == E2E_WARM:
-            h2d0, d2h0 = fgl.transfer_bytes()
-        t0 = time.perf_counter()
-        frame()
-        img = None
-        if world > 1:
-            img = group.read_frame()          # rank 0: the gathered frame in page-locked host memory; others: stream sync
-        else:
-            img = fgl.read_plane("ssaa_u8" if info["ssaa"] else "frame_u8", pinned=True)  # page-locked host buffer (fgl_host_alloc)
-        t1 = time.perf_counter()
-        _dbg("e2e step %d: %.3f ms" % (i, 1e3 * (t1 - t0)))
-        if i >= E2E_WARM:
-            e2e_t.append(t1 - t0)
-        elif i == 0 and rank == 0:  # the untimed first pass: fingerprint of the finished frame (must not depend on the number of GPUs)
+    for it in insts:  # untimed: allocates the page-locked frame buffers, fingerprints the frame of every instance
+        it.frame()
+        img = it.read()
+        if rank == 0:
             import hashlib
-            frame_hash = hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
-    h2d1, d2h1 = fgl.transfer_bytes()
-    h2d, d2h = (h2d1 - h2d0) // args.steps, (d2h1 - d2h0) // args.steps
+            h = hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
+            assert frame_hash in (None, h), "the instances in flight rendered different frames"
+            frame_hash = h
+    barrier()
+    tb0 = [it.fgl.transfer_bytes() for it in insts]
+    if flush_buf is None:
+        _, wall = run_frames(insts, args.steps, True, torch)
+        e2e_ms = 1e3 * wall / args.steps
+    else:
+        e2e_t = []
+        for _ in range(args.steps):
+            flush_l2()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            first.frame()
+            first.read()
+            e2e_t.append(time.perf_counter() - t0)
+        e2e_ms = 1e3 * sum(e2e_t) / len(e2e_t)
+    tb1 = [it.fgl.transfer_bytes() for it in insts]
+    h2d = sum(b[0] - a[0] for a, b in zip(tb0, tb1)) // args.steps
+    d2h = sum(b[1] - a[1] for a, b in zip(tb0, tb1)) // args.steps
     if world > 1 and rank == 0:
-        d2h += group.host_read_bytes
-    e2e_ms = 1e3 * sum(e2e_t) / len(e2e_t)
+        d2h += sum(it.group.host_read_bytes for it in insts) // max(1, len(insts))
     clocks = sampler.finish()
     _dbg("timed loops done: %.3f ms device, %.3f ms e2e" % (ms, e2e_ms))
 
-    # ---- per-kernel breakdown (library instrumentation, separate SERIALISED frames: no chain overlap while timing is on) ----
+    # ---- per-kernel breakdown (library instrumentation on ONE instance, separate SERIALISED frames: nothing overlaps while timing is on) ----
     barrier()
     fgl.enable_timing(True)
     fgl.reset_timings()
@@ -362,8 +451,8 @@ def run_ours(args):
         flush_l2()
         if world > 1:
             dist.barrier()  # keep the ranks within one frame of each other
-        frame(gather=False)
-    fgl.sync()
+        first.frame(gather=False)
+        first.sync()
     kern = fgl.timings()
     fgl.enable_timing(False)
     fgl.reset_timings()
@@ -384,7 +473,7 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
                 "avg_launch_ms": t_launch * 1e3, "share_of_frame": top["ms_per_frame"] / total_kernel_ms,
                 "limiter": LIMITERS.get(top["name"], "HBM bandwidth"), "counters": counters,
-                "note": "the kernel with the largest share of the frame; `frac` = its algorithmic bytes over time against the HBM peak "
+                "note": "the kernel with the largest share of a frame's kernel time; `frac` = its algorithmic bytes over time against the HBM peak "
                         "(a small value next to a non-HBM `limiter` means the kernel is not a bandwidth problem); per-kernel table in `kernels`"}
 
     if world > 1:
@@ -397,29 +486,36 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             factor, instance = reference_sample(args.workload, False)
-            times, cw, ch, what = time_reference(args.workload, 1, factor, instance)
-            cpu = {"value": cw * ch / 1e6 / times[0], "unit": "Mpixels/s", "cores": 1, "kind": "reference", "ms_per_frame": 1e3 * times[0],
+            times, cw2, ch2, what = time_reference(args.workload, 1, factor, instance)
+            cpu = {"value": cw2 * ch2 / 1e6 / times[0], "unit": "Mpixels/s", "cores": 1, "kind": "reference", "ms_per_frame": 1e3 * times[0],
                    "sample": "%s, 1 frame of oracle/_ref/ref_driver (the unmodified reference), single thread (the reference has no threads)" % what}
         line = {"metric": "mpixels_per_s", "value": out_px / 1e6 / (ms / 1e3), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "reference assets (obj/*) / generated C5 OBJ, camera and light of the scene file",
                 "config": config_of(args.workload, world),
                 "details": {"triangles": info["triangles"], "scene_load_s": round(info["load_s"], 2),
+                            "frames_in_flight": inflight,
+                            "frames_in_flight_note": ("%d independent frames are rendered concurrently (one facade instance, fgl context, CUDA stream and host thread each); "
+                                                      "ms_per_step is the time of K frames divided by K, the latency of a single frame is kernels[] summed" % inflight)
+                                                     if inflight > 1 else "one frame at a time",
                             "partition": group.describe() if group else "single GPU",
-                            "l2": "explicit 256 MiB flush between timed frames" if flush_buf is not None else "planes (%.0f MB per GPU) exceed the 126 MB L2" % (plane_bytes / 1e6)},
+                            "l2": "explicit 256 MiB flush between timed frames" if flush_buf is not None
+                                  else "a frame streams %.0f MB per GPU (planes + sample tables), far beyond the 126 MB L2" % (stream_bytes / 1e6)},
                 "frames_per_s": 1e3 / ms,
                 "e2e": {"value": out_px / 1e6 / (e2e_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "frame_sha256": frame_hash, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "single_frame_ms": round(sum(k["ms_per_frame"] for k in kern), 4),
                 "kernels": [{"name": k["name"], "ms_per_frame": round(k["ms_per_frame"], 4), "launches_per_frame": k["launches"] / nprof,
                              "share": round(k["ms_per_frame"] / total_kernel_ms, 4) if k["name"] not in waits else None,
                              "gbps": (k["algorithmic_bytes"] / max(1e-12, k["ms_total"] / 1e3) / 1e9) if k["algorithmic_bytes"] else None,
                              "limiter": LIMITERS.get(k["name"])}
                             for k in kern]}
         print(json.dumps(line), flush=True)
-    if group:
-        group.close()
-    info["free"]()
+    for it in insts:
+        if it.group:
+            it.group.close()
+        it.info["free"]()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -433,6 +529,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=0,
+                    help="frames rendered concurrently (each on its own facade instance / context / stream / host thread); 0 = default "
+                         "(2 on one GPU, 1 in a group); workloads small enough to need an L2 flush between frames always use 1")
     ap.add_argument("--group", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = band-split passes exchanged by peer stores over NVLink, device-side flags (default); "
                          "'nccl' = replicated shadow pass, RGB8 bands all-gathered with NCCL, chain state through the host")

@@ -429,12 +429,25 @@ CUDA_LIB = os.path.join(HERE, "libforkergl_b200.so")
 HOST_LIB = os.path.join(HERE, "libforkerhost.so")
 
 
-def product_host():
-    """The product: C++ facade over the CUDA library.  No fallback: raises if either is missing or no GPU."""
+def product_host(instance=0):
+    """The product: C++ facade over the CUDA library.  No fallback: raises if either is missing or no GPU.
+
+    instance > 0: a further, independent instance of the facade in this process (its own ForkerGL statics, scene and fgl
+    context) for frames in flight — the reference's API is a set of statics, so a second frame needs a second copy of the
+    library image: the shared object is loaded once more from a private copy of the file.  All instances share the one
+    libforkergl_b200.so."""
     for p in (CUDA_LIB, HOST_LIB):
         if not os.path.exists(p):
-            raise FglError("%s is missing — run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
-    return Host(HOST_LIB, CUDA_LIB)
+            raise FglError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
+    if instance == 0:
+        return Host(HOST_LIB)
+    import shutil
+    import tempfile
+    C.CDLL(CUDA_LIB, mode=C.RTLD_GLOBAL)  # the copy's DT_NEEDED entry resolves to the library that is already loaded
+    d = tempfile.mkdtemp(prefix="fgl_host_%d_" % instance)
+    copy = os.path.join(d, "libforkerhost_%d.so" % instance)
+    shutil.copy(HOST_LIB, copy)
+    return Host(copy)
 
 
 def product_fgl(device=0):

@@ -26,6 +26,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "stream.h"
 
@@ -1416,6 +1417,13 @@ static int scan_ints(fgl_ctx* c, const int* in, int* out, size_t n)
     return FGL_OK;
 }
 
+// Several contexts may share a device (frames in flight: one context per frame, each driven by its own host thread).  Two
+// persistent chain kernels must never be placed on the SMs at the same time — each needs a CTA on every SM, and two half-placed
+// grids would wait for each other at their first barrier — so the chain launches of a device are ordered behind one another:
+// every launch waits for the event recorded behind the previous one (whichever context issued it).
+static std::mutex  g_chainMutex;
+static cudaEvent_t g_chainDone[64] = { nullptr };
+
 // The persistent chain kernel: one CTA of 1024 threads per SM, grid-wide barriers on global counters.
 //   exclusive (shared = false): the 64-register build by a cooperative launch — co-residency guaranteed, the device is not
 //     shared with other kernels meanwhile;
@@ -1473,13 +1481,20 @@ static int launch_chain(fgl_ctx* c, SampleStream* s, ChainRows& R, int nU, size_
     int          pilotK = chain_pilot_k();
     void*        args[] = { &R, &state, &Ppre, &G8, &GM, &segLo, &rowBits, &rowLo, &flagU, &segsPerIter, &pilotK };
     // algorithmic bytes: every uncertain row's record once (45 B) + every chunk signature of the band once (8 B)
-    LaunchScope ls(c, "pcss_chain", (uint64_t)nU * 45 + ((uint64_t)n + 2ull * ((uint64_t)nC1 + (uint64_t)nU)) * 8);
-    if (coop) FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(1024), args, smemBytes, st));
-    else
+    std::lock_guard<std::mutex> chainOrder(g_chainMutex);
+    cudaEvent_t&                done = g_chainDone[c->device & 63];
+    if (done) FGL_CUDA(c, cudaStreamWaitEvent(st, done, 0));
+    else FGL_CUDA(c, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     {
-        kernel<<<grid, 1024, smemBytes, st>>>(R, state, Ppre, G8, GM, segLo, rowBits, rowLo, flagU, segsPerIter, pilotK);
-        FGL_CUDA(c, cudaGetLastError());
+        LaunchScope ls(c, "pcss_chain", (uint64_t)nU * 45 + ((uint64_t)n + 2ull * ((uint64_t)nC1 + (uint64_t)nU)) * 8);
+        if (coop) FGL_CUDA(c, cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(1024), args, smemBytes, st));
+        else
+        {
+            kernel<<<grid, 1024, smemBytes, st>>>(R, state, Ppre, G8, GM, segLo, rowBits, rowLo, flagU, segsPerIter, pilotK);
+            FGL_CUDA(c, cudaGetLastError());
+        }
     }
+    FGL_CUDA(c, cudaEventRecord(done, st));
     s->chainWasShared = shared;
     return FGL_OK;
 }
