@@ -431,7 +431,7 @@ void fgl_destroy(fgl_ctx* c)
     release(c->group.flags);
     fgl_stream_destroy(c);
     for (auto& p : c->planes) release(p.buf);
-    release(c->frameRgb8), release(c->ssaaRgb8), release(c->visCamera), release(c->visLight), release(c->texTable);
+    release(c->frameRgb8), release(c->ssaaRgb8), release(c->blurTmp), release(c->visCamera), release(c->visLight), release(c->texTable);
     release(c->drawsDev), release(c->setup), release(c->vary), release(c->zndc), release(c->nblk), release(c->blkScan), release(c->scanTmp), release(c->tileState);
     for (auto& b : c->preChunks) release(b);
     for (auto& t : c->textures) release(t.data);

@@ -183,7 +183,7 @@ struct fgl_ctx
     unsigned long long chainBlockersBefore = 0;  // sort-first: blockers found by the bands above this one (PCSS chain input)
 
     PlaneH planes[FGL_PLANE_AO + 1];
-    DevBuf frameRgb8, ssaaRgb8;
+    DevBuf frameRgb8, ssaaRgb8, blurTmp;
     bool   frameRgb8Valid = false, bandRgb8Valid = false;
     int    ssaaW = 0, ssaaH = 0;
 

@@ -212,19 +212,39 @@ __device__ __forceinline__ float blur_step(BlurState& s, float x0, float x1, flo
 
 // Both passes are bound by the recurrence itself: from y[w-1] to y[w] there is one multiply and seven dependent adds
 // (32 cycles; the summation order is part of the result), so a line of n samples costs >= 32 n cycles no matter how
-// wide the machine is.  The kernels therefore keep ONE walking warp per 32 lines fed from shared memory and hide all
-// global traffic behind it: a three-stage ring of tiles, the other seven warps load tile i and store tile i - 2
-// while warp 0 walks tile i - 1 (one __syncthreads per stage).  In-place hazards: a tile's look-ahead (4 samples past
-// its end) is read before the following tile is stored, exactly like the reference's loop reads not yet written data.
+// wide the machine is.  Parallelism therefore has to come from somewhere else:
+//   * lines are independent: a CTA owns 32 lines, ONE warp walks them (lane = line) out of shared memory while the other
+//     seven warps load tile i and store tile i - 2 (a three-stage ring, one __syncthreads per stage);
+//   * a line is cut into CHUNKS of kBlurChunk samples that run concurrently (grid.y).  A chunk that does not begin at the
+//     line's start walks kBlurWarm samples in front of its range first, from an arbitrary state: the recurrence forgets
+//     (its feedback weights sum to 0.386), so after the warm-up its four history values have — so far always — become
+//     bit-identical to the true ones.  That is CHECKED, not assumed: the chunk records the history it arrived with, and
+//     k_blur_check compares it with what the chunk in front of it really wrote; a line with a mismatch is flagged and
+//     recomputed serially by k_blur_fix.  If every boundary matches, every chunk continued from the exact state and the
+//     result is the reference's, bit for bit.
+// The passes are out of place (H: plane -> scratch, V: scratch -> plane), which is what lets a chunk read original
+// samples in front of its range while its neighbour is writing there; the reference's in-place loop reads exactly the same
+// mix (already blurred behind, still original ahead).
 constexpr int kBlurTW = 96, kBlurLD = kBlurTW + 5;  // H: tile width, row pitch (101 = 5 mod 32: conflict-free)
 constexpr int kBlurTR = 64;                         // V: tile rows
+constexpr int kBlurChunk = 768, kBlurWarmUp = 64;   // samples per chunk (a multiple of both tile sizes), warm-up samples
 
-__global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H, int rowBegin)
+struct BlurChunks
+{
+    int    begin, end;   // samples [begin, end) of every line are produced (begin > 0: a sort-first band's warm start, unchecked)
+    int    nChunks;
+    float* boundary;     // [line][chunk][4]: the history a chunk arrived with at its first sample (chunks >= 1)
+};
+
+__global__ void __launch_bounds__(256) k_blur_h(const float* src, float* dst, int W, int H, int rowBegin, BlurChunks C)
 {
     __shared__ float tile[3][32][kBlurLD];
     const int row0 = rowBegin + blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nT = (W + kBlurTW - 1) / kBlurTW;
+    const int chunk = blockIdx.y;
+    const int outBegin = C.begin + chunk * kBlurChunk, outEnd = min(C.end, outBegin + kBlurChunk);
+    const int walkBegin = chunk == 0 ? outBegin : max(0, outBegin - kBlurWarmUp);
+    const int nT = (outEnd - walkBegin + kBlurTW - 1) / kBlurTW;
     BlurState st;
     st.h1 = st.h2 = st.h3 = st.h4 = 0.f;
     for (int i = 0; i < nT + 2; ++i)
@@ -235,12 +255,17 @@ __global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H, int rowB
             if (k >= 0 && k < nT && row0 + lane < H)
             {
                 float* t = tile[k % 3][lane];
-                const int c0 = k * kBlurTW, tw = min(kBlurTW, W - c0);
+                const int c0 = walkBegin + k * kBlurTW, tw = min(kBlurTW, outEnd - c0);
                 if (k == 0) st.h1 = st.h2 = st.h3 = st.h4 = t[0];
                 float x0 = t[0], x1 = t[1], x2 = t[2], x3 = t[3];
 #pragma unroll 8
                 for (int j = 0; j < tw; ++j)
                 {
+                    if (chunk > 0 && c0 + j == outBegin)
+                    {
+                        float4* bq = reinterpret_cast<float4*>(C.boundary + ((size_t)(row0 + lane) * C.nChunks + chunk) * 4);
+                        *bq = make_float4(st.h1, st.h2, st.h3, st.h4);
+                    }
                     float x4 = t[j + 4];
                     float r = blur_step(st, x0, x1, x2, x3, x4, c0 + j == 0);
                     t[j] = r;
@@ -253,21 +278,22 @@ __global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H, int rowB
             const int ks = i - 2;
             if (ks >= 0)
             {
-                const int c0 = ks * kBlurTW, tw = min(kBlurTW, W - c0);
+                const int c0 = walkBegin + ks * kBlurTW, tw = min(kBlurTW, outEnd - c0);
                 for (int r = warp - 1; r < 32; r += 7)
                 {
                     int row = row0 + r;
                     if (row >= H) break;
-                    for (int j = lane; j < tw; j += 32) a[(size_t)row * W + c0 + j] = tile[ks % 3][r][j];
+                    for (int j = lane; j < tw; j += 32)
+                        if (c0 + j >= outBegin) dst[(size_t)row * W + c0 + j] = tile[ks % 3][r][j];
                 }
             }
             if (i < nT)
             {   // asynchronous copies (LDGSTS): all of a thread's loads are in flight at once, nothing is staged in registers
-                const int c0 = i * kBlurTW, tw4 = min(kBlurTW, W - c0) + 4;
+                const int c0 = walkBegin + i * kBlurTW, tw4 = min(kBlurTW, outEnd - c0) + 4;
                 for (int e = threadIdx.x - 32; e < 32 * tw4; e += 224)
                 {
                     int r = e / tw4, j = e - r * tw4, row = row0 + r;
-                    if (row < H) __pipeline_memcpy_async(&tile[i % 3][r][j], &a[(size_t)row * W + min(c0 + j, W - 1)], 4);
+                    if (row < H) __pipeline_memcpy_async(&tile[i % 3][r][j], &src[(size_t)row * W + min(c0 + j, W - 1)], 4);
                 }
                 __pipeline_commit();
             }
@@ -277,17 +303,20 @@ __global__ void __launch_bounds__(256) k_blur_h(float* a, int W, int H, int rowB
     }
 }
 
-// V pass: a CTA owns 32 columns, lane = column.  rowBegin > 0 (sort-first band): the recurrence is warmed up from a
-// row >= 64 above the band; its memory of the start decays as 0.61^n, far below fp32 resolution after 64 rows
-// (DESIGN.md §6).  Look-ahead rows past the bottom edge re-read the not yet overwritten last row, as the in-place
-// loop of the reference does.
-__global__ void __launch_bounds__(256) k_blur_v(float* a, int W, int H, int rowBegin, int rowEnd)
+// V pass: a CTA owns 32 columns, lane = column; chunks run along the rows.  C.begin > 0 (sort-first band): the first chunk
+// starts from a row >= 64 above the band as if it were the plane's first row; its memory of the start decays as 0.61^n, far
+// below fp32 resolution after 64 rows — the rows in front of the band belong to another GPU, so that one
+// warm-up cannot be checked here (the group's frame hash is).  Look-ahead rows past the bottom edge re-read the last row.
+__global__ void __launch_bounds__(256) k_blur_v(const float* src, float* dst, int W, int H, BlurChunks C)
 {
     __shared__ float tile[3][kBlurTR + 4][32];
     const int  warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int  x = blockIdx.x * 32 + lane;
     const bool colOk = x < W;
-    const int  nT = (rowEnd - rowBegin + kBlurTR - 1) / kBlurTR;
+    const int  chunk = blockIdx.y;
+    const int  outBegin = C.begin + chunk * kBlurChunk, outEnd = min(C.end, outBegin + kBlurChunk);
+    const int  walkBegin = chunk == 0 ? outBegin : max(0, outBegin - kBlurWarmUp);
+    const int  nT = (outEnd - walkBegin + kBlurTR - 1) / kBlurTR;
     BlurState  st;
     st.h1 = st.h2 = st.h3 = st.h4 = 0.f;
     for (int i = 0; i < nT + 2; ++i)
@@ -298,14 +327,19 @@ __global__ void __launch_bounds__(256) k_blur_v(float* a, int W, int H, int rowB
             if (k >= 0 && k < nT)
             {
                 float(*t)[32] = tile[k % 3];
-                const int r0 = rowBegin + k * kBlurTR, th = min(kBlurTR, rowEnd - r0);
+                const int r0 = walkBegin + k * kBlurTR, th = min(kBlurTR, outEnd - r0);
                 if (k == 0) st.h1 = st.h2 = st.h3 = st.h4 = t[0][lane];
                 float x0 = t[0][lane], x1 = t[1][lane], x2 = t[2][lane], x3 = t[3][lane];
 #pragma unroll 8
                 for (int j = 0; j < th; ++j)
                 {
+                    if (chunk > 0 && r0 + j == outBegin && colOk)
+                    {
+                        float4* bq = reinterpret_cast<float4*>(C.boundary + ((size_t)x * C.nChunks + chunk) * 4);
+                        *bq = make_float4(st.h1, st.h2, st.h3, st.h4);
+                    }
                     float x4 = t[j + 4][lane];
-                    float r = blur_step(st, x0, x1, x2, x3, x4, r0 + j == rowBegin);
+                    float r = blur_step(st, x0, x1, x2, x3, x4, chunk == 0 && r0 + j == C.begin);
                     t[j][lane] = r;
                     x0 = x1, x1 = x2, x2 = x3, x3 = x4;
                 }
@@ -316,19 +350,51 @@ __global__ void __launch_bounds__(256) k_blur_v(float* a, int W, int H, int rowB
             const int ks = i - 2;
             if (ks >= 0 && colOk)
             {
-                const int r0 = rowBegin + ks * kBlurTR, th = min(kBlurTR, rowEnd - r0);
-                for (int r = warp - 1; r < th; r += 7) a[(size_t)(r0 + r) * W + x] = tile[ks % 3][r][lane];
+                const int r0 = walkBegin + ks * kBlurTR, th = min(kBlurTR, outEnd - r0);
+                for (int r = warp - 1; r < th; r += 7)
+                    if (r0 + r >= outBegin) dst[(size_t)(r0 + r) * W + x] = tile[ks % 3][r][lane];
             }
             if (i < nT)
             {
-                const int r0 = rowBegin + i * kBlurTR, th = min(kBlurTR, rowEnd - r0);
+                const int r0 = walkBegin + i * kBlurTR, th = min(kBlurTR, outEnd - r0);
                 if (colOk)
-                    for (int r = warp - 1; r < th + 4; r += 7) __pipeline_memcpy_async(&tile[i % 3][r][lane], &a[(size_t)min(r0 + r, H - 1) * W + x], 4);
+                    for (int r = warp - 1; r < th + 4; r += 7) __pipeline_memcpy_async(&tile[i % 3][r][lane], &src[(size_t)min(r0 + r, H - 1) * W + x], 4);
                 __pipeline_commit();
             }
             __pipeline_wait_prior(0);
         }
         __syncthreads();
+    }
+}
+
+// boundary check: the four values in front of chunk k's first sample, as the chunk in front of it wrote them, against the
+// history chunk k arrived with (bit for bit).  stride: distance between consecutive samples of a line, pitch: between lines.
+__global__ void k_blur_check(const float* out, size_t stride, size_t pitch, int nLines, int lineBase, BlurChunks C, unsigned* lineFlags)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int line = i / C.nChunks, chunk = i - line * C.nChunks;
+    if (line >= nLines || chunk == 0) return;
+    const int     at = C.begin + chunk * kBlurChunk;
+    const float*  q = out + (size_t)(lineBase + line) * pitch;
+    const float4  h = *reinterpret_cast<const float4*>(C.boundary + ((size_t)(lineBase + line) * C.nChunks + chunk) * 4);
+    const bool    same = __float_as_uint(q[(size_t)(at - 1) * stride]) == __float_as_uint(h.x) && __float_as_uint(q[(size_t)(at - 2) * stride]) == __float_as_uint(h.y) &&
+                      __float_as_uint(q[(size_t)(at - 3) * stride]) == __float_as_uint(h.z) && __float_as_uint(q[(size_t)(at - 4) * stride]) == __float_as_uint(h.w);
+    if (!same) atomicOr(lineFlags + (lineBase + line), 1u);
+}
+// flagged lines, recomputed from their first sample by one thread each (never taken so far; keeps the result exact if it ever is)
+__global__ void k_blur_fix(const float* src, float* dst, size_t stride, size_t pitch, int nLines, int lineBase, int len, BlurChunks C, unsigned* lineFlags)
+{
+    int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= nLines || !lineFlags[lineBase + line]) return;
+    lineFlags[lineBase + line] = 0u;
+    const float* x = src + (size_t)(lineBase + line) * pitch;
+    float*       y = dst + (size_t)(lineBase + line) * pitch;
+    BlurState    st;
+    st.h1 = st.h2 = st.h3 = st.h4 = x[(size_t)C.begin * stride];
+    for (int w = C.begin; w < C.end; ++w)
+    {
+        auto at = [&](int k) { return x[(size_t)min(w + k, len - 1) * stride]; };
+        y[(size_t)w * stride] = blur_step(st, at(0), at(1), at(2), at(3), at(4), w == C.begin);
     }
 }
 
@@ -575,15 +641,40 @@ int fgl_run_blur(fgl_ctx* c, float* plane, int W, int H, int channels, int kind,
     }
     if (kind != FGL_BLUR_TWO_PASS_GAUSSIAN) return fgl_fail(c, FGL_ERR_INVALID, "fgl_blur: unknown blur kind");
     if (hRow1 <= hRow0 || vRow1 <= vRow0) return FGL_OK;
+    // scratch plane for the H pass + the chunks' boundary records and line flags
+    BlurChunks CH, CV;
+    CH.begin = 0, CH.end = W, CH.nChunks = (W + kBlurChunk - 1) / kBlurChunk;
+    CV.begin = vRow0, CV.end = vRow1, CV.nChunks = (vRow1 - vRow0 + kBlurChunk - 1) / kBlurChunk;
+    const size_t bndFloats = std::max((size_t)H * CH.nChunks, (size_t)W * CV.nChunks) * 4, nFlags = (size_t)std::max(W, H);
+    const size_t n4 = (n + 3) & ~(size_t)3;  // the boundary records are read as float4
+    if (int rc = fgl_reserve(c, c->blurTmp, n4 * 4 + bndFloats * 4 + nFlags * 4 + 64)) return rc;
+    float*    tmp = (float*)c->blurTmp.p;
+    float*    bnd = tmp + n4;
+    unsigned* flags = (unsigned*)(bnd + bndFloats);
+    CH.boundary = CV.boundary = bnd;
+    cudaStream_t st = c->stream;
     for (int ch = 0; ch < channels; ++ch)
     {
+        float* a = plane + ch * n;
+        if (cudaMemsetAsync(flags, 0, nFlags * 4, st) != cudaSuccess) return check_launch(c, "blur");
         {
-            LaunchScope ls(c, "blur_h", n * 8);
-            k_blur_h<<<(hRow1 - hRow0 + 31) / 32, 256, 0, c->stream>>>(plane + ch * n, W, hRow1, hRow0);
+            LaunchScope ls(c, "blur_h", (size_t)(hRow1 - hRow0) * W * 8);
+            k_blur_h<<<dim3((hRow1 - hRow0 + 31) / 32, CH.nChunks), 256, 0, st>>>(a, tmp, W, hRow1, hRow0, CH);
+            if (CH.nChunks > 1)
+            {
+                const int lines = hRow1 - hRow0;
+                k_blur_check<<<(lines * CH.nChunks + 255) / 256, 256, 0, st>>>(tmp, 1, (size_t)W, lines, hRow0, CH, flags);
+                k_blur_fix<<<(lines + 127) / 128, 128, 0, st>>>(a, tmp, 1, (size_t)W, lines, hRow0, W, CH, flags);
+            }
         }
         {
-            LaunchScope ls(c, "blur_v", n * 8);
-            k_blur_v<<<(W + 31) / 32, 256, 0, c->stream>>>(plane + ch * n, W, H, vRow0, vRow1);
+            LaunchScope ls(c, "blur_v", (size_t)(vRow1 - vRow0) * W * 8);
+            k_blur_v<<<dim3((W + 31) / 32, CV.nChunks), 256, 0, st>>>(tmp, a, W, H, CV);
+            if (CV.nChunks > 1)
+            {
+                k_blur_check<<<(W * CV.nChunks + 255) / 256, 256, 0, st>>>(a, (size_t)W, 1, W, 0, CV, flags);
+                k_blur_fix<<<(W + 127) / 128, 128, 0, st>>>(tmp, a, (size_t)W, 1, W, 0, H, CV, flags);
+            }
         }
     }
     return check_launch(c, "blur");
