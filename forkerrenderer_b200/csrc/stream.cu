@@ -343,6 +343,12 @@ __device__ __forceinline__ void rect_add(const ChainPass& P, float scx, float sc
     }
 }
 __global__ void k_rect_init(int* rect) { rect[0] = rect[1] = 0x7fffffff, rect[2] = rect[3] = -1; }
+// texels of the rectangle grown by the widest margin the box maps are built with (byte model of the min / max passes)
+__global__ void k_rect_area(const int* rect, int margin, int W, int H, unsigned* area)
+{
+    int x0 = max(0, rect[0] - margin), y0 = max(0, rect[1] - margin), x1 = min(W - 1, rect[2] + margin), y1 = min(H - 1, rect[3] + margin);
+    *area = (rect[2] < rect[0] || x1 < x0 || y1 < y0) ? 0u : (unsigned)(x1 - x0 + 1) * (unsigned)(y1 - y0 + 1);
+}
 
 // grid-stride: every thread keeps its rectangle in registers, a warp merges once at the end (four atomics per warp of the
 // whole launch — per-pixel atomics on four addresses would serialise in the L2)
@@ -1600,7 +1606,16 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     if (!prepared)
     {
     {
-        LaunchScope ls(c, "pcss_minmax", smN * 48);
+        // byte model: 48 B per texel the passes really produce (two box maps, two passes each) — the whole map, or the texel
+        // rectangle of the band's sites grown by the margin, counted on the device
+        const unsigned* areaPtr = nullptr;
+        if (s->rectValid)
+        {
+            unsigned* area = (unsigned*)s->rect.p + 4;
+            k_rect_area<<<1, 1, 0, st>>>((const int*)s->rect.p, 3 * r + 2, L.sm.w, L.sm.h, area);
+            areaPtr = area;
+        }
+        LaunchScope ls(c, "pcss_minmax", areaPtr ? 0 : smN * 48, areaPtr, 48);
         auto box = [&](int lo, int hi, float* omin, float* omax, int margin) -> int {
             const int w = hi - lo + 1;
             MapRegion region;
@@ -1812,7 +1827,7 @@ int fgl_stream_prepare_lighting(fgl_ctx* c, LightPass& L, int phase)
         s->rectValid = pcss && !noRect;
         if (s->rectValid)
         {
-            if (int rc = fgl_reserve(c, s->rect, 16)) return rc;
+            if (int rc = fgl_reserve(c, s->rect, 32)) return rc;
             P.fsF = pcss_filter_bound(L.pcssFilter);
             k_rect_init<<<1, 1, 0, c->stream>>>((int*)s->rect.p);
         }
