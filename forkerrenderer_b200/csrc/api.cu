@@ -247,7 +247,7 @@ int flush(fgl_ctx* c)
         size_t rows = (size_t)(P.cull1 - P.cull0);
         LaunchScope ls(c, "vis_clear", rows * P.W * 8);
         if (rows) FGL_CUDA(c, cudaMemsetAsync((char*)vis.p + (size_t)P.cull0 * P.W * 8, 0xFF, rows * P.W * 8, c->stream));
-        visClear = true;  // (the rest of the buffer still holds old keys: a later stand-alone pass clears everything)
+        visClear = false;  // (rows outside the band keep old keys; fgl_group_disconnect schedules a full clear for stand-alone passes)
     }
     else if (visClear)
     {
@@ -1114,6 +1114,13 @@ static int plane_as_aos(fgl_ctx* c, int plane, const void** src, size_t* bytes)
         if (int rc = fgl_reserve(c, c->scanTmp, *bytes)) return rc;
         if (int rc = fgl_run_aos(c, (const float*)p.buf.p, (float*)c->scanTmp.p, n, p.ch, true)) return rc;
         *src = c->scanTmp.p;
+        return FGL_OK;
+    }
+    if (plane == FGL_PLANE_FRAME_RGB8 && c->group.on)
+    {   // the 8-bit frame of a sort-first group lives on rank 0, its rows are stored there by every band's lighting kernel
+        if (c->group.rank != 0) return fgl_fail(c, FGL_ERR_STATE, "the 8-bit frame of a sort-first group is gathered on rank 0");
+        if (int rc = fgl_group_wait(c, FGL_GROUP_BAND)) return rc;
+        *src = c->group.expRgb8, *bytes = (size_t)c->group.W * c->group.H * 3;
         return FGL_OK;
     }
     if (plane == FGL_PLANE_FRAME_RGB8)

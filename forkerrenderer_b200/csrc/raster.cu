@@ -375,17 +375,21 @@ __global__ void __launch_bounds__(128) k_raster_small(RasterPass P, int primBegi
     }
 }
 
-template <int MODE>
+// kLanesPerItem lanes share one work item (a 32 x 32 block of one triangle's bounding box).  32: a lane per column — the
+// few huge triangles of the reference's scenes (the ground plane) fill their blocks.  8: four items per warp — most blocks of a
+// high-triangle-count pass are a few pixels wide, and the per-item part (search, set-up record, the double-precision edge
+// set-up) is shared by the lanes of an item; a lane then walks the columns l8, l8 + 8, ... of the block.
+template <int MODE, int kLanesPerItem>
 __global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBegin, int nNew, const int* tileBase)
 {
-    const int lane = threadIdx.x & 31;
-    const int warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    const int l8 = threadIdx.x & (kLanesPerItem - 1);
+    const int groupsPerGrid = (gridDim.x * blockDim.x) / kLanesPerItem;
     const int nTiles = (nNew + kSetupTile - 1) / kSetupTile;
     const int total = tileBase[nTiles];
     int       cachedTri = -1, cachedBegin = 0, cachedEnd = 0;
     SetupRegs s;
     TriCover  tc;
-    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warpsPerGrid)
+    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) / kLanesPerItem; item < total; item += groupsPerGrid)
     {
         if (item < cachedBegin || item >= cachedEnd)
         {   // last tile whose first item is <= item, then the last triangle of that tile whose first item is <= item
@@ -414,15 +418,21 @@ __global__ void __launch_bounds__(256) k_raster_blocks(RasterPass P, int primBeg
         int local = item - cachedBegin;
         int nbx = (s.xmax - s.xmin + kBlk) / kBlk;
         int bx = local % nbx, by = local / nbx;
-        int px = s.xmin + bx * kBlk + lane;
+        int x0 = s.xmin + bx * kBlk, x1 = min(x0 + kBlk - 1, s.xmax);
         int y0 = s.ymin + by * kBlk, y1 = min(y0 + kBlk - 1, s.ymax);
-        if (px > s.xmax) continue;
+        if (x0 + l8 > x1) continue;
         bool    sane = s.flags & 8;
-        EdgeInt e = make_edges(s, px, y0);
-        for (int py = y0; py <= y1; ++py)
+        EdgeInt col = make_edges(s, x0 + l8, y0);
+        for (int px = x0 + l8; px <= x1; px += kLanesPerItem)  // (a single trip with a lane per column)
         {
-            if (!sane || (e.e0 | e.e1 | e.e2) >= 0) depth_test_pixel<MODE, false>(P, tc, s, cachedTri, px, py);
-            e.e0 += e.dy0, e.e1 += e.dy1, e.e2 += e.dy2;
+            long long e0 = col.e0, e1 = col.e1, e2 = col.e2;
+            for (int py = y0; py <= y1; ++py)
+            {
+                if (!sane || (e0 | e1 | e2) >= 0) depth_test_pixel<MODE, false>(P, tc, s, cachedTri, px, py);
+                e0 += col.dy0, e1 += col.dy1, e2 += col.dy2;
+            }
+            if (kLanesPerItem == kBlk) break;
+            col.e0 += kLanesPerItem * col.dx0, col.e1 += kLanesPerItem * col.dx1, col.e2 += kLanesPerItem * col.dx2;
         }
     }
 }
@@ -755,12 +765,12 @@ int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t*
         if (mode == RM_COUNT)
         {
             k_raster_small<RM_COUNT><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
-            k_raster_blocks<RM_COUNT><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims, tileBase);
+            k_raster_blocks<RM_COUNT, 32><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims, tileBase);
         }
         else
         {
             k_raster_small<RM_FILL><<<(nPrims + 127) / 128, 128, 0, st>>>(P, 0);
-            k_raster_blocks<RM_FILL><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims, tileBase);
+            k_raster_blocks<RM_FILL, 32><<<c->numSMs * 8, 256, 0, st>>>(P, 0, nPrims, tileBase);
         }
         ++c->launches;
     };
@@ -858,7 +868,9 @@ int fgl_run_raster(fgl_ctx* c, const RasterPass& P, PlanesD planes, uint8_t* rgb
         }
         {
             LaunchScope ls(c, "raster_blocks", 0);
-            k_raster_blocks<RM_DEPTH><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew, tileBase);
+            // passes with many triangles: mostly small blocks, eight lanes each; few triangles: the big ones dominate
+            if (smallArea > 0) k_raster_blocks<RM_DEPTH, 8><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew, tileBase);
+            else k_raster_blocks<RM_DEPTH, 32><<<c->numSMs * 8, 256, 0, st>>>(P, primBegin, nNew, tileBase);
         }
     }
     // sort-first group: the resolves store into the other contexts' planes — not before those have begun this frame

@@ -28,6 +28,19 @@ def test_reference_arm_prints_one_json_line():
     assert (d["config"]["width"], d["config"]["height"]) == (1280, 800)
 
 
+def test_reference_arm_of_the_scaling_workload_uses_the_same_config():
+    """--gpus N > 1 defaults to C5; the reference arm reports C5's config and says which bounded sample it timed."""
+    if not P.have_ref():
+        pytest.skip("oracle/_ref/ref_driver not built")
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
+    assert (d["config"]["width"], d["config"]["height"], d["config"]["gpus"]) == (7680, 4320, 2) and "10 008 338" in d["config"]["workload"]
+    assert "c5_golden" in d["cpu_baseline"]["sample"] and d["value"] > 0
+
+
 def test_product_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import parity as P
+from conftest import sha
 from forkerrenderer_b200 import binding as B
 from forkerrenderer_b200 import multigpu as M
 from forkerrenderer_b200.synthetic import SyntheticScene
@@ -85,3 +86,40 @@ def test_band_planes_read_back_cleared_outside_the_band(gpu_fgl):
         assert np.array_equal(f.read_plane("depth"), full["depth"])  # SSAO gathers depth from anywhere: resolved everywhere
     finally:
         f.close()
+
+
+def test_group_of_one_is_the_standalone_frame(gpu_host, golden):
+    """The sort-first group code path (fgl_group_export / connect: band-restricted passes, peer stores — here into the context's
+    own planes — epoch flags, rank 0's gathered 8-bit frame) with a group of ONE on this GPU: every plane must be the
+    stand-alone frame's, bit for bit, and carry the reference's fingerprints.  (tools/group_check.py does the same with 2 - 8
+    processes on as many GPUs.)"""
+    import os
+    cfg = "c1_ssao_pcss"
+    scene, shadow, wrap, filt = P.CONFIGS[cfg]
+    sc = gpu_host.load_scene(os.path.join(P.REPO, scene), P.ASSETS, wrap, filt)
+    names = ["depth", "shadow", "normal", "worldpos", "lightndc", "ao", "frame", "ids_camera"]
+    try:
+        gpu_host.render(sc, shadow, True)
+        f = gpu_host.fgl
+        alone = {n: f.read_plane(n).copy() for n in names + ["frame_u8"]}
+        member = gpu_host.group_export(sc)
+        gpu_host.group_connect(0, 1, [member], same_process=True)
+        try:
+            for _ in range(2):
+                gpu_host.render(sc, shadow, True)
+                img = gpu_host.group_read_frame(sc.height, sc.width)
+                assert np.array_equal(img, alone["frame_u8"])
+                assert np.array_equal(f.read_plane("frame_u8"), alone["frame_u8"])
+                for n in names:
+                    assert P.bits_equal(f.read_plane(n), alone[n]), n
+            with pytest.raises(B.FglError):
+                f.set_row_band(0, 10)  # the band follows from the rank
+        finally:
+            gpu_host.group_disconnect()
+        gpu_host.render(sc, shadow, True)  # and back to a stand-alone context
+        assert np.array_equal(f.read_plane("frame_u8"), alone["frame_u8"])
+        want = golden[cfg]["planes"]
+        for n in ("depth", "shadow", "ao", "ids_camera"):
+            assert sha(f.read_plane(n)) == want[n]["sha256"], n
+    finally:
+        sc.free()
