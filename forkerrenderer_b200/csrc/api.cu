@@ -853,9 +853,9 @@ int fgl_draw_mesh(fgl_ctx* c, int meshId, int kind, const FglUniforms* un)
 
 // Device copy of a host array that has to stay alive until the pass ends (draws are deferred): chunks are only ever added
 // while a pass is open, so pointers already recorded in draw commands stay valid.
-static int stash(fgl_ctx* c, const float* src, size_t bytes, const float** out)
+static int stash(fgl_ctx* c, const float* src, size_t srcBytes, const float** out)
 {
-    bytes = (bytes + 255) & ~(size_t)255;
+    const size_t bytes = (srcBytes + 255) & ~(size_t)255;  // slots are 256-byte aligned; only srcBytes are read from the caller
     if (c->preChunks.empty() || c->preUsed + bytes > c->preChunks.back().cap)
     {
         DevBuf b;
@@ -866,9 +866,9 @@ static int stash(fgl_ctx* c, const float* src, size_t bytes, const float** out)
         c->preUsed = 0;
     }
     char* dst = (char*)c->preChunks.back().p + c->preUsed;
-    FGL_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    FGL_CUDA(c, cudaMemcpyAsync(dst, src, srcBytes, cudaMemcpyHostToDevice, c->stream));
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller's arrays may be gone when this call returns
-    c->h2dBytes += bytes;
+    c->h2dBytes += srcBytes;
     c->preUsed += bytes;
     *out = (const float*)dst;
     return FGL_OK;

@@ -1,6 +1,9 @@
 // geometry.cpp — host-side matrix builders with the reference's exact expression order.
-// Restates (not copies) reference src/geometry.cpp:60-68, 92-145, 166-179 and the cofactor-expansion
-// determinant / inverse of src/geometry.h:604-742.  See geometry.h for the rules.
+// The four builders (model, look-at, perspective, orthographic; reference src/geometry.cpp:92-179) are TRANSCRIBED: the uniforms
+// they produce have to equal the reference's bit for bit, and for these five-line textbook formulas
+// that means the same expressions in the same order (checked word for word against the reference, tests/test_host_math.py).
+// The normal matrix (src/geometry.cpp:60-68) and the cofactor-expansion determinant / inverse (src/geometry.h:604-742) are
+// written afresh around the same evaluation tree.  See geometry.h for the rules.
 #include "geometry.h"
 
 namespace

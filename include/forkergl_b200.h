@@ -205,7 +205,9 @@ int fgl_get_chain_blockers(fgl_ctx* ctx, uint64_t* out_blockers);
  *   fgl_group_connect  members[0..world) = the records of all contexts in rank order (this context's own at [rank]).
  *                      EVERY context must have returned from fgl_group_connect before any of them begins a frame.
  *                      From then on Render::Render (or the raw pass calls) on this context renders its band; all contexts
- *                      must render the same sequence of frames.  Deferred mode only; SSAA is not available in a group.
+ *                      must render the same sequence of frames.  Deferred mode only; SSAA is not available in a group; every
+ *                      raster pass of a group frame is submitted whole (one flush) and has at least one triangle (a pass
+ *                      without any would never signal its rows to the other bands: they report a time-out after 30 s).
  *   fgl_group_read_frame  rank 0: waits (on the device) for every band of the current frame, then copies the 8-bit frame
  *                      (FGL_PLANE_FRAME_RGB8 layout) to host memory; other ranks: FGL_ERR_STATE
  *   fgl_group_disconnect  back to a stand-alone context */
