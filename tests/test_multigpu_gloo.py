@@ -139,6 +139,72 @@ def test_peer_handoff_setup_and_fallback(oracle_fgl):
         oracle_fgl.chain_peer_mailbox()
 
 
+class FakeGroupHost:
+    """Stand-in for the facade's group entry points (frh_group_*): records what the Python driver asks for."""
+
+    def __init__(self, rank):
+        self.rank, self.log, self.fgl = rank, [], self
+
+    def group_export(self, scene):
+        self.log.append("export")
+        return bytes([self.rank]) * 368
+
+    def group_connect(self, rank, world, members, same_process=False):
+        self.log.append(("connect", rank, world, [m[0] for m in members], len(members[0])))
+
+    def render(self, scene, shadow_mode, materialize):
+        self.log.append("render")
+
+    def group_read_frame(self, h, w):
+        self.log.append("read")
+        return np.zeros((h, w, 3), dtype=np.uint8)
+
+    def group_disconnect(self):
+        self.log.append("disconnect")
+
+    def sync(self):
+        self.log.append("sync")
+
+
+def group_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Scene:
+        deferred, ssaa = True, False
+
+    class R:
+        height, width, pcss, shadow_mode, materialize = 10, 8, True, "pcss", False
+    host = FakeGroupHost(rank)
+    R.host, R.scene = host, Scene()
+    g = M.Group(host, dist, rank, world, R, mode="peer")
+    g.render_frame()
+    img = g.read_frame()
+    g.close()
+    connect = [e for e in host.log if isinstance(e, tuple)]
+    ok = (host.log[0] == "export" and len(connect) == 1 and connect[0][1:4] == (rank, world, list(range(world))) and connect[0][4] == 368
+          and host.log.count("render") == 1 and ((img is not None and "read" in host.log) if rank == 0 else (img is None and "read" not in host.log))
+          and host.log[-1] == "disconnect" and "peers' memory" in g.describe())
+    out.put((rank, ok, host.log if not ok else None))
+    dist.destroy_process_group()
+
+
+def test_peer_group_rendezvous_hands_every_rank_all_members_in_rank_order():
+    """multigpu.Group(mode='peer'): the only host-side communication of the C++ / CUDA group is the exchange of the member
+    records (rank order) and a barrier; rendering is frh_render on every rank, rank 0 alone reads the gathered frame."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=group_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+
+
 def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
