@@ -252,12 +252,19 @@ class Instance:
         self.fgl.set_stream(self.stream.cuda_stream)
         self.group = M.Group(self.fgl, dist, rank, world, self.r, mode=args.group) if world > 1 else None
         self.image = None
+        # frames without host read-backs (hard / PCF shadows) go through frh_render_replay: recorded once as a CUDA graph, then
+        # one launch per frame; PCSS frames (the default workloads) cannot be recorded and keep the eager calls
+        self.replay = args.replay != "off" and world == 1 and WORKLOADS[args.workload][1] != "pcss"
+        self.replayed = 0
 
-    def frame(self, gather=True):
+    def frame(self, gather=True, eager=False):
         """One frame; with several GPUs: this rank's band (chain hand-off and gather of the 8-bit rows happen on the devices)."""
         with self.torch.cuda.stream(self.stream):
             if self.world > 1:
                 return self.group.render_frame(gather=gather)
+            if self.replay and not eager:
+                self.replayed += int(self.r.replay())
+                return None
             self.r.begin((0, -1))
             self.r.finish()
         return None
@@ -451,7 +458,7 @@ def run_ours(args):
         flush_l2()
         if world > 1:
             dist.barrier()  # keep the ranks within one frame of each other
-        first.frame(gather=False)
+        first.frame(gather=False, eager=True)
         first.sync()
     kern = fgl.timings()
     fgl.enable_timing(False)
@@ -495,6 +502,9 @@ def run_ours(args):
                 "config": config_of(args.workload, world),
                 "details": {"triangles": info["triangles"], "scene_load_s": round(info["load_s"], 2),
                             "frames_in_flight": inflight,
+                            "graph_replay": ("%d of the frames were launches of the recorded CUDA graph (frh_render_replay)" % sum(it.replayed for it in insts))
+                                            if first.replay else "off (PCSS frames read chain state back to the host and cannot be recorded)",
+                            "graph_replay_fallback": first.r.host.replay_fallback_reason() if first.replay else None,
                             "frames_in_flight_note": ("%d independent frames are rendered concurrently (one facade instance, fgl context, CUDA stream and host thread each); "
                                                       "ms_per_step is the time of K frames divided by K, the latency of a single frame is kernels[] summed" % inflight)
                                                      if inflight > 1 else "one frame at a time",
@@ -532,6 +542,9 @@ def main():
     ap.add_argument("--inflight", type=int, default=0,
                     help="frames rendered concurrently (each on its own facade instance / context / stream / host thread); 0 = default "
                          "(2 on one GPU, 1 in a group); workloads small enough to need an L2 flush between frames always use 1")
+    ap.add_argument("--replay", default="auto", choices=["auto", "off"],
+                    help="auto: hard-shadow / PCF workloads on one GPU are rendered through frh_render_replay (the frame recorded once as a "
+                         "CUDA graph, then one launch per frame); off: always the eager facade calls")
     ap.add_argument("--group", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = band-split passes exchanged by peer stores over NVLink, device-side flags (default); "
                          "'nccl' = replicated shadow pass, RGB8 bands all-gathered with NCCL, chain state through the host")

@@ -276,6 +276,24 @@ class Fgl:
     def copy_plane_rows_to_device(self, plane, y0, y1, dst_ptr, nbytes):
         self.call("fgl_copy_plane_rows_to_device", int(plane), int(y0), int(y1), C.c_void_p(dst_ptr), nbytes)
 
+    # ---- recorded frames (CUDA graphs)
+    def frame_record_begin(self): self.call("fgl_frame_record_begin")
+
+    def frame_record_end(self, frame_id=-1):
+        v = C.c_int(int(frame_id))
+        self.call("fgl_frame_record_end", C.byref(v))
+        return v.value
+
+    def frame_record_abort(self): self.call("fgl_frame_record_abort")
+    def frame_replay(self, frame_id): self.call("fgl_frame_replay", int(frame_id))
+    def frame_release(self, frame_id): self.call("fgl_frame_release", int(frame_id))
+
+    def frame_info(self, frame_id):
+        """(graph nodes, kernel launches) of one replay."""
+        a, b = C.c_int(0), C.c_int(0)
+        self.call("fgl_frame_info", int(frame_id), C.byref(a), C.byref(b))
+        return a.value, b.value
+
     # ---- instrumentation
     def enable_timing(self, on=True): self.call("fgl_enable_timing", int(on))
     def reset_timings(self): self.call("fgl_reset_timings")
@@ -357,6 +375,21 @@ class Host:
         if isinstance(shadow_mode, str):
             shadow_mode = SHADOW_MODES[shadow_mode]
         self._ck(self.lib.frh_render(scene.handle, int(shadow_mode), int(bool(materialize_frame_f32))), "frh_render")
+
+    def render_replay(self, scene, shadow_mode=SHADOW_PCSS, materialize_frame_f32=True):
+        """frh_render_replay: the frame as a recorded CUDA graph (first call eager, second call records + replays, then one
+        graph launch per call).  Returns True if this call was a graph launch; frames that cannot be recorded are rendered
+        eagerly (replay_fallback_reason() says why)."""
+        if isinstance(shadow_mode, str):
+            shadow_mode = SHADOW_MODES[shadow_mode]
+        done = C.c_int(0)
+        self.lib.frh_render_replay.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self._ck(self.lib.frh_render_replay(scene.handle, int(shadow_mode), int(bool(materialize_frame_f32)), C.byref(done)), "frh_render_replay")
+        return bool(done.value)
+
+    def replay_fallback_reason(self):
+        self.lib.frh_replay_fallback_reason.restype = C.c_char_p
+        return self.lib.frh_replay_fallback_reason().decode()
 
     def render_begin(self, scene, shadow_mode=SHADOW_PCSS, materialize_frame_f32=True):
         if isinstance(shadow_mode, str):

@@ -18,9 +18,17 @@ int fgl_fail(fgl_ctx* c, int code, const std::string& msg)
     return code;
 }
 
+int fgl_not_while_recording(fgl_ctx* c, const char* what)
+{
+    if (!c || !c->recording) return FGL_OK;
+    return fgl_fail(c, FGL_ERR_UNSUPPORTED, std::string(what) + " cannot be part of a recorded frame (fgl_frame_record_begin .. fgl_frame_record_end)");
+}
+
 int fgl_reserve(fgl_ctx* c, DevBuf& b, size_t bytes)
 {
     if (bytes <= b.cap) return FGL_OK;
+    if (c && c->recording)
+        return fgl_fail(c, FGL_ERR_UNSUPPORTED, "a device buffer would have to grow while a frame is being recorded: render the same frame once without recording first");
     size_t want = std::max(bytes, b.cap + b.cap / 2);
     void*  p = nullptr;
     if (cudaMalloc(&p, want) != cudaSuccess)
@@ -28,6 +36,11 @@ int fgl_reserve(fgl_ctx* c, DevBuf& b, size_t bytes)
         cudaGetLastError();
         if (cudaMalloc(&p, bytes) != cudaSuccess) return fgl_fail(c, FGL_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
         want = bytes;
+    }
+    if (b.p && c)
+    {   // recorded frames have the old address baked into their graphs
+        for (auto& f : c->recorded)
+            if (f.exec) cudaGraphExecDestroy(f.exec), f.exec = nullptr;
     }
     if (b.p)
     {   // growth keeps the contents (a pass can be flushed more than once)
@@ -69,6 +82,8 @@ void fgl_time_end(fgl_ctx* c) { cudaEventRecord(c->timings.back().e1, c->stream)
 
 namespace
 {
+constexpr size_t kRecStagingBytes = (size_t)4 << 20;  // page-locked staging of one recorded frame's draw commands
+
 #define ENTER(c)                                                      \
     if (!(c)) return FGL_ERR_INVALID;                                 \
     if (cudaSetDevice((c)->device) != cudaSuccess) return fgl_fail((c), FGL_ERR_CUDA, "cudaSetDevice failed")
@@ -147,6 +162,7 @@ PlanesD planes_dev(fgl_ctx* c)
 int upload_tex_table(fgl_ctx* c)
 {
     if (!c->texTableDirty) return FGL_OK;
+    if (int rc = fgl_not_while_recording(c, "the upload of a changed texture table")) return rc;
     std::vector<TexD> t(std::max<size_t>(1, c->textures.size()));
     for (size_t i = 0; i < c->textures.size(); ++i) t[i] = c->textures[i].desc;
     if (int rc = fgl_reserve(c, c->texTable, t.size() * sizeof(TexD))) return rc;
@@ -257,8 +273,24 @@ int flush(fgl_ctx* c)
     }
     int nPrims = c->primCounter, nNew = nPrims - c->flushedPrims;
     if (int rc = fgl_reserve(c, c->drawsDev, c->draws.size() * sizeof(DrawCmdD))) return rc;
-    FGL_CUDA(c, cudaMemcpyAsync(c->drawsDev.p, c->draws.data(), c->draws.size() * sizeof(DrawCmdD), cudaMemcpyHostToDevice, c->stream));
-    c->h2dBytes += c->draws.size() * sizeof(DrawCmdD);
+    {
+        const size_t drawBytes = c->draws.size() * sizeof(DrawCmdD);
+        const void*  src = c->draws.data();
+        if (c->recording)
+        {   // a replay re-reads the host side of this copy: it has to live as long as the recorded frame does
+            const size_t slot = (drawBytes + 255) & ~(size_t)255;
+            if (c->recStagingUsed + slot > kRecStagingBytes)
+            {
+                c->flushedPrims = c->primCounter;
+                return fgl_fail(c, FGL_ERR_UNSUPPORTED, "too many draw commands for a recorded frame");
+            }
+            memcpy((char*)c->recStaging + c->recStagingUsed, src, drawBytes);
+            src = (char*)c->recStaging + c->recStagingUsed;
+            c->recStagingUsed += slot;
+        }
+        FGL_CUDA(c, cudaMemcpyAsync(c->drawsDev.p, src, drawBytes, cudaMemcpyHostToDevice, c->stream));
+        c->h2dBytes += drawBytes;
+    }
     if (int rc = fgl_reserve(c, c->setup, (size_t)nPrims * sizeof(TriSetup))) return rc;
     if (shadowPass) { if (int rc = fgl_reserve(c, c->zndc, (size_t)nPrims * sizeof(float4))) return rc; }
     else if (int rc = fgl_reserve(c, c->vary, (size_t)nPrims * sizeof(TriVary))) return rc;
@@ -359,6 +391,38 @@ void retire_empty_pass(fgl_ctx* c)
     c->depthInitPending = false;
 }
 
+void save_host_state(const fgl_ctx* c, RecordedFrame::HostState& h)
+{
+    static_assert(FGL_PLANE_AO + 1 <= 16, "HostState::planes");
+    for (int i = 0; i <= FGL_PLANE_AO; ++i)
+    {
+        const PlaneH& p = c->planes[i];
+        auto&         q = h.planes[i];
+        q.w = p.w, q.h = p.h, q.ch = p.ch, q.fillPending = p.fillPending, q.fillIsRGB = p.fillIsRGB, q.fillPartial = p.fillPartial, q.fillValue = p.fillValue;
+        memcpy(q.fillRGB, p.fillRGB, sizeof q.fillRGB);
+        q.validRow0 = p.validRow0, q.validRow1 = p.validRow1;
+    }
+    h.frameRgb8Valid = c->frameRgb8Valid, h.bandRgb8Valid = c->bandRgb8Valid, h.visCamClear = c->visCamClear, h.visLightClear = c->visLightClear;
+    h.depthInitPending = c->depthInitPending, h.depthInitBound = c->depthInitBound, h.passRestarted = c->passRestarted;
+    h.ssaaW = c->ssaaW, h.ssaaH = c->ssaaH, h.visCamW = c->visCamW, h.visCamH = c->visCamH, h.visLightW = c->visLightW, h.visLightH = c->visLightH;
+    h.pass = c->pass, h.primCounter = c->primCounter, h.flushedPrims = c->flushedPrims;
+}
+void restore_host_state(fgl_ctx* c, const RecordedFrame::HostState& h)
+{
+    for (int i = 0; i <= FGL_PLANE_AO; ++i)
+    {
+        PlaneH&     p = c->planes[i];
+        const auto& q = h.planes[i];
+        p.w = q.w, p.h = q.h, p.ch = q.ch, p.fillPending = q.fillPending, p.fillIsRGB = q.fillIsRGB, p.fillPartial = q.fillPartial, p.fillValue = q.fillValue;
+        memcpy(p.fillRGB, q.fillRGB, sizeof p.fillRGB);
+        p.validRow0 = q.validRow0, p.validRow1 = q.validRow1;
+    }
+    c->frameRgb8Valid = h.frameRgb8Valid, c->bandRgb8Valid = h.bandRgb8Valid, c->visCamClear = h.visCamClear, c->visLightClear = h.visLightClear;
+    c->depthInitPending = h.depthInitPending, c->depthInitBound = h.depthInitBound, c->passRestarted = h.passRestarted;
+    c->ssaaW = h.ssaaW, c->ssaaH = h.ssaaH, c->visCamW = h.visCamW, c->visCamH = h.visCamH, c->visLightW = h.visLightW, c->visLightH = h.visLightH;
+    c->pass = h.pass, c->primCounter = h.primCounter, c->flushedPrims = h.flushedPrims;
+}
+
 int ensure_rgb8(fgl_ctx* c)
 {
     if (c->frameRgb8Valid) return FGL_OK;
@@ -439,6 +503,19 @@ void fgl_destroy(fgl_ctx* c)
     for (auto& m : c->meshes) release(m.pi), release(m.ti), release(m.ni);
     for (auto& t : c->timings) cudaEventDestroy(t.e0), cudaEventDestroy(t.e1);
     for (auto& e : c->eventPool) cudaEventDestroy(e);
+    if (c->recording)
+    {   // an unfinished recording: close the capture so that the stream can be destroyed
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(c->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+    }
+    if (c->recStaging) cudaFreeHost(c->recStaging);
+    for (auto& f : c->recorded)
+    {
+        if (f.exec) cudaGraphExecDestroy(f.exec);
+        if (f.staging) cudaFreeHost(f.staging);
+    }
     cudaStreamDestroy(c->ownStream);
     delete c;
 }
@@ -449,6 +526,7 @@ const char* fgl_backend_name(void) { return "cuda-sm_100a"; }
 int fgl_set_stream(fgl_ctx* c, void* s)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_set_stream")) return rc;
     if (int rc = flush(c)) return rc;
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = s ? (cudaStream_t)s : c->ownStream;
@@ -466,6 +544,7 @@ int fgl_set_params(fgl_ctx* c, const FglParams* p)
 int fgl_sync(fgl_ctx* c)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_sync")) return rc;
     if (int rc = flush(c)) return rc;
     if (c->chainStream) FGL_CUDA(c, cudaStreamSynchronize(c->chainStream));
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -484,6 +563,7 @@ static int upload(fgl_ctx* c, DevBuf& b, const void* src, size_t bytes)
 int fgl_upload_texture(fgl_ctx* c, const uint8_t* texels, int w, int h, int bpp, int wrap, int filter, int* id)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_upload_texture")) return rc;
     if (!texels || w <= 0 || h <= 0 || (bpp != 1 && bpp != 3 && bpp != 4) || !id || wrap < 0 || wrap > 3 || filter < 0 || filter > 1)
         return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_texture: bad arguments");
     TextureH t;
@@ -498,6 +578,7 @@ int fgl_upload_texture(fgl_ctx* c, const uint8_t* texels, int w, int h, int bpp,
 int fgl_upload_vertices(fgl_ctx* c, const float* pos, int np, const float* uv, int nt, const float* nrm, int nn, const float* tan, int ntan, int* id)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_upload_vertices")) return rc;
     if (!id || np < 0 || nt < 0 || nn < 0 || ntan < 0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_vertices: bad arguments");
     VerticesH v;
     v.nPos = pos ? np : 0, v.nUv = uv ? nt : 0, v.nNrm = nrm ? nn : 0, v.nTan = tan ? ntan : 0;
@@ -514,6 +595,7 @@ int fgl_upload_mesh(fgl_ctx* c, int vid, int nFaces, const int* pi, const int* t
                     int supportPBR, int* id)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_upload_mesh")) return rc;
     if (!id || !mat || vid < 0 || vid >= (int)c->vertices.size() || nFaces < 0 || (nFaces && (!pi || !ti || !ni)))
         return fgl_fail(c, FGL_ERR_INVALID, "fgl_upload_mesh: bad arguments");
     const VerticesH& vb = c->vertices[vid];
@@ -666,6 +748,7 @@ int fgl_set_chain_blockers_before(fgl_ctx* c, uint64_t blockers)
 int fgl_get_chain_blockers(fgl_ctx* c, uint64_t* out)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_get_chain_blockers")) return rc;
     if (!out) return fgl_fail(c, FGL_ERR_INVALID, "out is NULL");
     unsigned long long v = 0;
     if (int rc = fgl_stream_chain_total(c, &v)) return rc;
@@ -698,6 +781,7 @@ int fgl_set_row_band(fgl_ctx* c, int row0, int row1)
 int fgl_group_export(fgl_ctx* c, int w, int h, FglGroupMember* out)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_group_export")) return rc;
     if (!out || w <= 0 || h <= 0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_group_export: bad arguments");
     if (int rc = flush(c)) return rc;
     if (c->group.on) return fgl_fail(c, FGL_ERR_STATE, "fgl_group_export: disconnect the current group first");
@@ -731,6 +815,7 @@ int fgl_group_export(fgl_ctx* c, int w, int h, FglGroupMember* out)
 int fgl_group_connect(fgl_ctx* c, int rank, int world, const FglGroupMember* m, int sameProcess)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_group_connect")) return rc;
     if (!m || world < 1 || world > kMaxGroup || rank < 0 || rank >= world) return fgl_fail(c, FGL_ERR_INVALID, "fgl_group_connect: bad arguments");
     if (int rc = flush(c)) return rc;
     GroupState& g = c->group;
@@ -877,6 +962,7 @@ static int stash(fgl_ctx* c, const float* src, size_t srcBytes, const float** ou
 int fgl_draw_triangles(fgl_ctx* c, int meshId, int kind, const FglUniforms* un, int n, const float* ndc, const float* vary, const float* lightZ)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_draw_triangles (its arrays are copied synchronously)")) return rc;
     if (!un || meshId < 0 || meshId >= (int)c->meshes.size() || n < 0 || (n && !ndc)) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: bad arguments");
     if (kind < FGL_SHADER_DEPTH || kind > FGL_SHADER_PBR) return fgl_fail(c, FGL_ERR_INVALID, "fgl_draw_triangles: bad shader kind");
     if (c->pass == FGL_PASS_GEOMETRY && kind != FGL_SHADER_G)
@@ -1154,6 +1240,7 @@ static int plane_as_aos(fgl_ctx* c, int plane, const void** src, size_t* bytes)
 int fgl_read_plane(fgl_ctx* c, int plane, void* dst, size_t bytes)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_read_plane")) return rc;
     if (plane < 0 || plane >= FGL_PLANE_COUNT || !dst) return fgl_fail(c, FGL_ERR_INVALID, "fgl_read_plane: bad arguments");
     if (int rc = flush(c)) return rc;
     const void* src = nullptr;
@@ -1184,6 +1271,7 @@ int fgl_host_free(fgl_ctx* c, void* p)
 int fgl_write_plane(fgl_ctx* c, int plane, const void* src, size_t bytes)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_write_plane")) return rc;
     if (plane < 0 || plane > FGL_PLANE_AO || !src) return fgl_fail(c, FGL_ERR_INVALID, "fgl_write_plane: bad arguments");
     if (int rc = flush(c)) return rc;
     PlaneH& p = c->planes[plane];
@@ -1206,6 +1294,7 @@ int fgl_write_plane(fgl_ctx* c, int plane, const void* src, size_t bytes)
 int fgl_copy_plane_rows_to_device(fgl_ctx* c, int plane, int row0, int row1, void* dst, size_t bytes)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_copy_plane_rows_to_device")) return rc;
     if (plane < 0 || plane >= FGL_PLANE_COUNT || !dst || row0 < 0 || row1 < row0) return fgl_fail(c, FGL_ERR_INVALID, "fgl_copy_plane_rows_to_device: bad arguments");
     if (int rc = flush(c)) return rc;
     int w, h, ch, bpc;
@@ -1227,11 +1316,174 @@ int fgl_copy_plane_rows_to_device(fgl_ctx* c, int plane, int row0, int row1, voi
     return FGL_OK;
 }
 
+// ---- recorded frames (SURVEY.md §8 f, N4: multi-frame use) ----------------------------------------------------------------
+// A frame without host read-backs is a fixed sequence of copies, clears and kernels on one stream: captured once into a CUDA
+// graph, it is replayed with a single launch.  Nothing is executed while recording; every entry point that would have to wait
+// for the device or allocate refuses (fgl_not_while_recording), and the recording then ends with an error instead of a graph.
+int fgl_frame_record_begin(fgl_ctx* c)
+{
+    ENTER(c);
+    if (c->recording) return fgl_fail(c, FGL_ERR_STATE, "fgl_frame_record_begin: already recording");
+    if (c->group.on) return fgl_fail(c, FGL_ERR_UNSUPPORTED, "a context of a sort-first group cannot record frames (its kernels wait for other GPUs)");
+    if (c->timing) return fgl_fail(c, FGL_ERR_UNSUPPORTED, "switch per-kernel timing off before recording a frame");
+    if (int rc = flush(c)) return rc;
+    if (c->chainEventPending)
+    {   // (an event of another stream recorded outside the capture cannot be waited for inside it)
+        FGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->evChainDone, 0));
+        c->chainEventPending = false;
+    }
+    if (!c->recStaging) FGL_CUDA(c, cudaHostAlloc(&c->recStaging, kRecStagingBytes, cudaHostAllocDefault));
+    c->recStagingUsed = 0;
+    c->recLaunches0 = c->launches, c->recH2d0 = c->h2dBytes;
+    // relaxed: other host threads (frames in flight on other contexts) keep calling CUDA while this thread records
+    FGL_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->recording = true;
+    return FGL_OK;
+}
+
+int fgl_frame_record_end(fgl_ctx* c, int* frameId)
+{
+    ENTER(c);
+    if (!c->recording) return fgl_fail(c, FGL_ERR_STATE, "fgl_frame_record_end without fgl_frame_record_begin");
+    int         rcFlush = flush(c);  // triangles still pending belong to the frame
+    std::string why = rcFlush ? c->error : std::string();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->recording = false;
+    RecordedFrame::HostState hs;
+    save_host_state(c, hs);
+    const uint64_t launches = c->launches - c->recLaunches0, h2d = c->h2dBytes - c->recH2d0;
+    c->launches = c->recLaunches0, c->h2dBytes = c->recH2d0;  // nothing has run yet: replays are counted when they are issued
+    // host-side bookkeeping now describes a frame that has not been rendered: make the next eager pass start clean
+    c->visCamClear = c->visLightClear = true;
+    c->frameRgb8Valid = c->bandRgb8Valid = false;
+    if (e != cudaSuccess || !graph || rcFlush)
+    {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return fgl_fail(c, FGL_ERR_UNSUPPORTED, "the frame could not be recorded: " + (why.empty() ? std::string(cudaGetErrorString(e)) : why));
+    }
+    if (!frameId)
+    {
+        cudaGraphDestroy(graph);
+        return fgl_fail(c, FGL_ERR_INVALID, "fgl_frame_record_end: frame_id is NULL");
+    }
+    size_t nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nodes);
+    RecordedFrame* f = nullptr;
+    if (*frameId >= 0)
+    {
+        if (*frameId >= (int)c->recorded.size() || !c->recorded[*frameId].staging)
+        {
+            cudaGraphDestroy(graph);
+            return fgl_fail(c, FGL_ERR_INVALID, "fgl_frame_record_end: no such recorded frame");
+        }
+        f = &c->recorded[*frameId];
+        // a replay of the old recording may still be reading its staging
+        cudaStreamSynchronize(c->stream);
+        cudaGraphExecUpdateResultInfo info;
+        memset(&info, 0, sizeof info);
+        if (f->exec && cudaGraphExecUpdate(f->exec, graph, &info) != cudaSuccess)
+        {   // another shape (a pass more or less): instantiate afresh
+            cudaGetLastError();
+            cudaGraphExecDestroy(f->exec);
+            f->exec = nullptr;
+        }
+        if (f->staging) cudaFreeHost(f->staging);
+        f->staging = nullptr;
+    }
+    else
+    {
+        c->recorded.emplace_back();
+        f = &c->recorded.back();
+        *frameId = (int)c->recorded.size() - 1;
+    }
+    if (!f->exec)
+    {
+        e = cudaGraphInstantiate(&f->exec, graph, 0);
+        if (e != cudaSuccess)
+        {
+            cudaGraphDestroy(graph);
+            f->exec = nullptr;
+            return fgl_fail(c, FGL_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaGraphDestroy(graph);
+    f->staging = c->recStaging, c->recStaging = nullptr;  // the graph's copy nodes read from it at every replay
+    f->launches = launches, f->h2dBytes = h2d, f->nodes = nodes, f->host = hs;
+    return FGL_OK;
+}
+
+int fgl_frame_record_abort(fgl_ctx* c)
+{
+    ENTER(c);
+    if (!c->recording) return FGL_OK;
+    cudaGraph_t graph = nullptr;
+    cudaStreamEndCapture(c->stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    c->recording = false;
+    c->launches = c->recLaunches0, c->h2dBytes = c->recH2d0;
+    // whatever the aborted sequence left pending or marked valid never happened
+    c->draws.clear();
+    c->primCounter = c->flushedPrims = 0;
+    c->visCamClear = c->visLightClear = true;
+    c->depthInitPending = c->depthInitBound = false;
+    c->frameRgb8Valid = c->bandRgb8Valid = false;
+    return FGL_OK;
+}
+
+int fgl_frame_replay(fgl_ctx* c, int frameId)
+{
+    ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_frame_replay")) return rc;
+    if (frameId < 0 || frameId >= (int)c->recorded.size() || !c->recorded[frameId].staging) return fgl_fail(c, FGL_ERR_INVALID, "fgl_frame_replay: no such recorded frame");
+    if (!c->recorded[frameId].exec)
+        return fgl_fail(c, FGL_ERR_STATE, "fgl_frame_replay: a device buffer was re-allocated after this frame was recorded (another frame size?): record it again");
+    if (c->group.on) return fgl_fail(c, FGL_ERR_UNSUPPORTED, "fgl_frame_replay: not inside a sort-first group");
+    if (int rc = flush(c)) return rc;
+    const RecordedFrame& f = c->recorded[frameId];
+    FGL_CUDA(c, cudaGraphLaunch(f.exec, c->stream));
+    c->launches += f.launches, c->h2dBytes += f.h2dBytes;
+    restore_host_state(c, f.host);  // the planes now hold the recorded frame
+    c->draws.clear();
+    return FGL_OK;
+}
+
+int fgl_frame_release(fgl_ctx* c, int frameId)
+{
+    ENTER(c);
+    if (frameId < 0 || frameId >= (int)c->recorded.size()) return fgl_fail(c, FGL_ERR_INVALID, "fgl_frame_release: no such recorded frame");
+    RecordedFrame& f = c->recorded[frameId];
+    cudaStreamSynchronize(c->stream);
+    if (f.exec) cudaGraphExecDestroy(f.exec);
+    if (f.staging) cudaFreeHost(f.staging);
+    f = RecordedFrame();
+    return FGL_OK;
+}
+
+int fgl_frame_info(fgl_ctx* c, int frameId, int* nodes, int* launches)
+{
+    ENTER(c);
+    if (frameId < 0 || frameId >= (int)c->recorded.size() || !c->recorded[frameId].staging) return fgl_fail(c, FGL_ERR_INVALID, "fgl_frame_info: no such recorded frame");
+    if (nodes) *nodes = (int)c->recorded[frameId].nodes;
+    if (launches) *launches = (int)c->recorded[frameId].launches;
+    return FGL_OK;
+}
+
 // ---- instrumentation ---------------------------------------------------------------------------------------------------
-int fgl_enable_timing(fgl_ctx* c, int on) { ENTER(c); c->timing = on != 0; return FGL_OK; }
+int fgl_enable_timing(fgl_ctx* c, int on)
+{
+    ENTER(c);
+    if (on)
+        if (int rc = fgl_not_while_recording(c, "per-kernel event timing")) return rc;
+    c->timing = on != 0;
+    return FGL_OK;
+}
 int fgl_reset_timings(fgl_ctx* c)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_reset_timings")) return rc;
     cudaStreamSynchronize(c->stream);
     for (auto& t : c->timings) c->eventPool.push_back(t.e0), c->eventPool.push_back(t.e1);
     c->timings.clear();
@@ -1240,6 +1492,7 @@ int fgl_reset_timings(fgl_ctx* c)
 int fgl_get_timings(fgl_ctx* c, FglTiming* out, int max, int* count)
 {
     ENTER(c);
+    if (int rc = fgl_not_while_recording(c, "fgl_get_timings")) return rc;
     FGL_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<std::string> order;
     std::map<std::string, FglTiming> agg;

@@ -81,6 +81,13 @@ FGL_HD V4 vdivs4(V4 a, float f)
 }
 FGL_HD float vlength(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }  // geometry.h:370-371
 FGL_HD V3    vnormalize(V3 a) { return vdivs(a, vlength(a)); }                   // geometry.h:906-910 (v*1 is exact)
+// SSAO (render.cpp:255-259): the scale of a hemisphere sample, Lerp(0.1f, 1.0f, len * len) with the reference's argument order.
+// A function of the sample alone (and the same for v and -v), so the sample table stores it next to the vector.
+FGL_HD float ssao_sample_scale(V3 v)
+{
+    float sc = vlength(v);
+    return (1 - 0.1f) * 1.0f + 0.1f * (sc * sc);
+}
 FGL_HD V3    vcross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 FGL_HD float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(v, lo)); }  // utility.h:32-35
 FGL_HD int   clampi(int v, int lo, int hi) { return min(hi, max(v, lo)); }
@@ -259,7 +266,11 @@ FGL_D float shadow_lookup(const ShadowMapD& sm, float u, float v)
 // powf: the reference calls glibc powf (correctly rounded in all but rare cases).  CUDA's powf is within a few
 // ulp of it, which only moves 8-bit colours that sit on a quantisation boundary (DESIGN.md "tolerances").
 FGL_D float fgl_pow(float a, float b) { return powf(a, b); }
-FGL_D V3    vpow(V3 v, float p) { return v3(fgl_pow(v.x, p), fgl_pow(v.y, p), fgl_pow(v.z, p)); }
+// The gamma conversions (exponents 2.2 and 1 / 2.2: positive, not odd integers): pow(+-0, y) is +0 by definition, in glibc and in
+// CUDA alike, so a zero base needs no evaluation — emissive colours are zero almost everywhere and background pixels are zero
+// in every channel, which makes this three to nine of a pixel's ten powf calls.
+FGL_D float fgl_pow_gamma(float a, float p) { return a == 0.f ? 0.f : powf(a, p); }
+FGL_D V3    vpow(V3 v, float p) { return v3(fgl_pow_gamma(v.x, p), fgl_pow_gamma(v.y, p), fgl_pow_gamma(v.z, p)); }
 FGL_D V3    vclamp01(V3 v) { return v3(clampf(v.x, 0.f, 1.f), clampf(v.y, 0.f, 1.f), clampf(v.z, 0.f, 1.f)); }
 
 struct LightConsts

@@ -167,6 +167,25 @@ struct TimingRec
     uint64_t        lateBytesEach = 0;
 };
 
+// A frame recorded as a CUDA graph (include/forkergl_b200.h "fgl_frame_*"): the instantiated graph, the page-locked staging
+// its host-to-device copies read from at every replay, and what one replay amounts to for the counters.
+struct RecordedFrame
+{
+    cudaGraphExec_t exec = nullptr;
+    void*           staging = nullptr;
+    uint64_t        launches = 0, h2dBytes = 0;
+    size_t          nodes = 0;
+    // the context's host-side bookkeeping as the recorded call sequence left it (restored by every replay, so that the context
+    // looks exactly as it does after rendering the frame eagerly): plane sizes and pending clears, validity of the 8-bit
+    // images, the visibility buffers' sizes, the pass state
+    struct HostState
+    {
+        struct Plane { int w, h, ch; bool fillPending, fillIsRGB, fillPartial; float fillValue, fillRGB[3]; int validRow0, validRow1; } planes[16];
+        bool frameRgb8Valid, bandRgb8Valid, visCamClear, visLightClear, depthInitPending, depthInitBound, passRestarted;
+        int  ssaaW, ssaaH, visCamW, visCamH, visLightW, visLightH, pass, primCounter, flushedPrims;
+    } host;
+};
+
 struct fgl_ctx
 {
     int          device = 0, numSMs = 148;  // SM count of the device (persistent grids are sized in multiples of it)
@@ -220,6 +239,13 @@ struct fgl_ctx
     uint64_t               launches = 0, h2dBytes = 0, d2hBytes = 0;
     GroupState             group;
     int                    lastUncertain = 0, lastChainIters = 0;  // PCSS: uncertain pixels / super-chunks of the last chain (diagnostics)
+
+    // frame recording (CUDA graph capture of the context's stream)
+    bool                       recording = false;
+    void*                      recStaging = nullptr;  // page-locked arena the recorded host-to-device copies read from
+    size_t                     recStagingUsed = 0;
+    uint64_t                   recLaunches0 = 0, recH2d0 = 0;
+    std::vector<RecordedFrame> recorded;
 };
 
 // error helpers ------------------------------------------------------------------------------------------------
@@ -233,6 +259,9 @@ int fgl_fail(fgl_ctx* c, int code, const std::string& msg);
     } while (0)
 
 int  fgl_reserve(fgl_ctx* c, DevBuf& b, size_t bytes);  // grow-only device allocation
+// Steps that synchronise with the host or allocate cannot be part of a recorded frame:
+//   if (int rc = fgl_not_while_recording(c, "...")) return rc;
+int  fgl_not_while_recording(fgl_ctx* c, const char* what);
 bool fgl_time_begin(fgl_ctx* c, const char* name, uint64_t bytes, const unsigned* lateCount, uint64_t lateBytesEach);
 void fgl_time_end(fgl_ctx* c);
 
@@ -281,6 +310,6 @@ struct SsaoPass
     float        radius, rangeCheckRadius, bias;
     int          rangeCheck;
     int          backgroundIsOne;  // set by fgl_run_ssao: background pixels are exactly AO = 1 (see k_ssao)
-    const float* ball;  // accepted unit-ball samples: x,y,z triples, 32 per pixel
+    const float4* ball;  // accepted unit-ball samples, 32 per pixel: x, y, z and the sample's scale (ssao_sample_scale)
 };
 int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S);

@@ -740,6 +740,7 @@ __global__ void __launch_bounds__(128) k_site_coords(RasterPass P, LightPass L, 
 // shadow coordinates.  Re-runs the raster loops in counting / recording mode over all triangles of the pass.
 int fgl_run_forward_sites(fgl_ctx* c, RasterPass& P, const LightPass& L, size_t* nSitesOut, const float4** sc4Out)
 {
+    if (int rc = fgl_not_while_recording(c, "a forward pass with a stochastic shadow filter (fragment counts are read back)")) return rc;
     cudaStream_t st = c->stream;
     size_t       nPix = (size_t)P.W * P.H;
     int          nPrims = P.nPrims;

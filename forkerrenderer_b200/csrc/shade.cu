@@ -471,6 +471,10 @@ __global__ void __launch_bounds__(1024) k_simple_blur(float* a, int W, int H, in
 //    [2][3]; with finite x, y, z the reference's row products ((0 + m0 x) + m1 y) + m2 z) + m3 w reduce to
 //    (0 + m_k v_k) + m3 w bit for bit (adding 0 * finite = +-0 to a sum that is +0 or non-zero changes nothing), and
 //    the w row is never used.  float -> int: cvttss2si only differs from a plain truncation outside +-2^31 (INT_MIN).
+//    The same variant drops the "0 +" every Dot of the reference starts with (geometry.h:774-793): 0 + a differs from a only
+//    for a = -0, and a sum whose LAST term is not -0 comes out the same whichever zero the partial sum carried (non-zero
+//    term: t; +0: +0).  The last terms are viewProj[r][3] * 1 and viewport[r][3] * ndc.w with ndc.w > 0 or NaN; the host
+//    selects this variant only when none of those seven matrix entries is -0.
 //    Both shortcuts are taken by the whole warp or not at all (one vote per pixel instead of a branch per sample).
 //  * background pixels (nothing drawn: depth = FLT_MAX, position = normal = 0) with the range check on: every sample sits
 //    within the SSAO radius of the world origin; when the host has verified that the projection of that ball is finite
@@ -490,16 +494,18 @@ __global__ void __launch_bounds__(256) k_ssao(SsaoPass S)
     const unsigned last = min(first + kSsaoPPW, end);
     const float    inf = __int_as_float(0x7f800000);
     // accepted unit-ball sample number 32 * pixel + lane of the replayed stream (geometry.h:957-966)
-    const float* b = S.ball + ((size_t)first * 32 + lane) * 3;
-    V3           vNext = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
+    // (one 16-byte record: the vector and its scale Lerp(0.1, 1, |v|^2), which k_compact computed with this kernel's arithmetic)
+    const float4* b = S.ball + ((size_t)first * 32 + lane);
+    float4        qNext = __ldcs(b);
     for (unsigned idx = first; idx < last; ++idx)
     {
-        V3 v = vNext;
+        const float4 q = qNext;
         if (idx + 1 < last)
         {
-            b += 96;
-            vNext = v3(__ldcs(b), __ldcs(b + 1), __ldcs(b + 2));
+            b += 32;
+            qNext = __ldcs(b);
         }
+        V3 v = v3(q.x, q.y, q.z);
         const float fragDepth = S.depth[idx];
         const float* wp = S.worldpos + idx;
         const V3     pos = v3(wp[0], wp[n], wp[2 * (size_t)n]);
@@ -510,18 +516,28 @@ __global__ void __launch_bounds__(256) k_ssao(SsaoPass S)
         }
         const float* np = S.normal + idx;
         const V3     nrm = v3(np[0], np[n], np[2 * (size_t)n]);
-        if (!(vdot(v, nrm) > 0.f)) v = v3(-v.x, -v.y, -v.z);  // geometry.h:978-990
-        float sc = vlength(v);
-        sc = (1 - 0.1f) * 1.0f + 0.1f * (sc * sc);  // Lerp(0.1f, 1.0f, sc * sc) with the reference's argument order
-        v = vscale(v, sc);
+        // geometry.h:978-990.  Dot starts its sum at 0: "0 + a" differs from a only for a = -0, which can only change the SIGN of a
+        // zero sum — invisible to the comparison
+        if (!((v.x * nrm.x + v.y * nrm.y) + v.z * nrm.z > 0.f)) v = v3(-v.x, -v.y, -v.z);
+        v = vscale(v, q.w);  // q.w = ssao_sample_scale(v): Lerp(0.1f, 1.0f, |v|^2), unchanged by the flip
         V3 sp = vadd(pos, vscale(v, S.radius));
         V4 sp4;
         sp4.x = sp.x, sp4.y = sp.y, sp4.z = sp.z, sp4.w = 1.f;
-        V4 cs = mat4mul(S.viewProj, sp4);
+        V4 cs;
+        if (VIEWPORT_AFFINE)
+        {   // the rows' last terms (m[r][3] * 1) are not -0 (host check): the leading "0 +" of Dot cannot change the sums
+            const float* m = S.viewProj;
+            cs.x = ((m[0] * sp.x + m[1] * sp.y) + m[2] * sp.z) + m[3];
+            cs.y = ((m[4] * sp.x + m[5] * sp.y) + m[6] * sp.z) + m[7];
+            cs.z = ((m[8] * sp.x + m[9] * sp.y) + m[10] * sp.z) + m[11];
+            cs.w = ((m[12] * sp.x + m[13] * sp.y) + m[14] * sp.z) + m[15];
+        }
+        else cs = mat4mul(S.viewProj, sp4);
         V4 ndc = vdivs4(cs, cs.w);
-        float ssx = (0.f + S.viewport[0] * ndc.x) + S.viewport[3] * ndc.w;
-        float ssy = (0.f + S.viewport[5] * ndc.y) + S.viewport[7] * ndc.w;
-        float ssz = (0.f + S.viewport[10] * ndc.z) + S.viewport[11] * ndc.w;
+        // (ndc.w = cs.w * (1 / cs.w) is positive or NaN, so the second term has the sign of the viewport entry: not -0 either)
+        float ssx = S.viewport[0] * ndc.x + S.viewport[3] * ndc.w;
+        float ssy = S.viewport[5] * ndc.y + S.viewport[7] * ndc.w;
+        float ssz = S.viewport[10] * ndc.z + S.viewport[11] * ndc.w;
         int   sx = (int)ssx, sy = (int)ssy;
         const bool plain = VIEWPORT_AFFINE && fabsf(ndc.x) < inf && fabsf(ndc.y) < inf && fabsf(ndc.z) < inf && fabsf(ssx) < 1.0e9f && fabsf(ssy) < 1.0e9f;
         if (!__all_sync(0xffffffffu, plain))
@@ -684,9 +700,11 @@ int fgl_run_ssao(fgl_ctx* c, const SsaoPass& S)
 {
     size_t      nPix = (size_t)S.W * (S.row1 - S.row0);
     if (!nPix) return FGL_OK;
-    LaunchScope ls(c, "ssao", nPix * (32 + 384));
+    LaunchScope ls(c, "ssao", nPix * (32 + 512));
     const float* m = S.viewport;  // ForkerGL::SetViewportMatrix structure (rows 0-2; the w row is not used by SSAO)
-    const bool   affine = m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f;
+    auto         negZero = [](float f) { return f == 0.f && std::signbit(f); };
+    const bool   affine = m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f && !negZero(m[3]) && !negZero(m[7]) &&
+                        !negZero(m[11]) && !negZero(S.viewProj[3]) && !negZero(S.viewProj[7]) && !negZero(S.viewProj[11]) && !negZero(S.viewProj[15]);
     // Background shortcut (see k_ssao): a sample of a background pixel lies within R = 1.0001 * radius of the world origin
     // (|v| < 1, scale in [0.9, 1]).  Its clip-space w = (a, b, c) . P + d is at least |d| - R (|a| + |b| + |c|) in magnitude
     // (less a rounding margin); if that is comfortably positive and every row of the matrix stays far from overflow, the

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) k_compact(const uint32_t* raw, size_t nCa
     if (!a) return;
     unsigned long long g = *accBase + (unsigned long long)tileOffsets[blockIdx.x] + (unsigned long long)rank;
     if (g >= need) return;
-    if (K == 3) out[g * 3] = x, out[g * 3 + 1] = y, out[g * 3 + 2] = z;
+    if (K == 3) reinterpret_cast<float4*>(out)[g] = make_float4(x, y, z, ssao_sample_scale(v3(x, y, z)));  // one 16-byte record per ball sample
     else out[g * 2] = x, out[g * 2 + 1] = y;
     if (g == need - 1) *rawEnd = rawBase + (unsigned long long)K * (cand + 1);
 }
@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(256) k_chain_pilot(ChainRows R, int* pilot, in
     if (valid) pilot[j] = cnt;
 }
 
-enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_ARRIVE = 4, CH_EPOCH = 5, CH_ERROR = 6, CH_ARRIVE_ROWS = 7, CH_NBLOCKERS = 8, CH_NFILTERED = 9 };
+enum { CH_J0 = 0, CH_M0 = 1, CH_DONE = 2, CH_ITERS = 3, CH_ARRIVE = 4, CH_EPOCH = 5, CH_ERROR = 6, CH_ARRIVE_ROWS = 7, CH_NBLOCKERS = 8, CH_NFILTERED = 9,
+       CH_PACKED = 12 /* 64-bit, 8-byte aligned: the state the CTAs wait for, in one word (see chain_pack) */ };
 
 // ---- the chain as ONE persistent cooperative kernel ----------------------------------------------------------------
 // A super-chunk is cut into segments of kSeg = 32 rows.  Per iteration (one super-chunk from an exactly known state):
@@ -602,8 +603,37 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// The state a super-chunk starts from travels from CTA 0 to the other CTAs as ONE 64-bit word, so that the load that sees the
+// new epoch also carries the state (three more dependent L2 round trips per iteration otherwise):
+//   bits 0..21 j0 / 32 (j0 is a multiple of the segment size until the chain is done), 22..48 m0, 49 done, 50..63 epoch mod 2^14.
+// A waiter knows exactly which epoch comes next, so the truncated epoch is compared for equality.
+constexpr int      kChainMaxRowsLog2 = 27;  // launch_chain refuses more uncertain rows than the fields hold
+constexpr unsigned kEpochMask = 0x3fffu;
+__device__ __forceinline__ unsigned long long chain_pack(unsigned j0, unsigned m0, bool done, unsigned epoch)
+{
+    return (unsigned long long)(j0 >> 5) | ((unsigned long long)m0 << 22) | ((unsigned long long)(done ? 1u : 0u) << 49) |
+           ((unsigned long long)(epoch & kEpochMask) << 50);
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+// spins until the packed state carries `epoch`; gives up (returns false) after ~2 s
+__device__ __forceinline__ bool spin_packed(const unsigned long long* p, unsigned epoch, unsigned long long& w)
+{
+    const long long t0 = clock64();
+    while ((unsigned)((w = ld_acquire_u64(p)) >> 50) != (epoch & kEpochMask))
+    {
+        __nanosleep(20);
+        if (clock64() - t0 > 4000000000LL) return false;
+    }
+    return true;
+}
 
 // spins until *p >= want; gives up (returns false) after ~2 s so a broken launch can never hang the device
 __device__ __forceinline__ bool spin_until(const unsigned* p, unsigned want)
@@ -682,11 +712,15 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
     {
         if (threadIdx.x == 0)
         {
-            bool ok = true;
-            if (blockIdx.x != 0 && it > 0) ok = spin_until(state + CH_EPOCH, it);
-            sCtl[0] = (int)ld_acquire_u32(state + CH_J0), sCtl[1] = (int)ld_acquire_u32(state + CH_M0);
-            sCtl[2] = ok ? (int)ld_acquire_u32(state + CH_DONE) : 1;
-            if (!ok) atomicExch(state + CH_ERROR, 1u);
+            if (it == 0) sCtl[0] = 0, sCtl[1] = 0, sCtl[2] = 0;  // (the host zeroed the state)
+            else if (blockIdx.x != 0)
+            {   // CTA 0 left the next state in its own sCtl when it published it
+                unsigned long long w = 0ull;
+                const bool         ok = spin_packed(reinterpret_cast<const unsigned long long*>(state + CH_PACKED), it, w);
+                sCtl[0] = (int)(((unsigned)w & 0x3fffffu) << 5), sCtl[1] = (int)((unsigned)(w >> 22) & 0x7ffffffu);
+                sCtl[2] = ok ? (int)((w >> 49) & 1ull) : 1;
+                if (!ok) atomicExch(state + CH_ERROR, 1u);
+            }
         }
         __syncthreads();
         if (sCtl[2]) return;
@@ -939,8 +973,7 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
             if (threadIdx.x == 0)
             {
                 atomicExch(state + CH_ERROR, 2u), atomicExch(state + CH_DONE, 1u);
-                __threadfence();
-                st_release_u32(state + CH_EPOCH, 0x7fffffffu);
+                st_release_u64(reinterpret_cast<unsigned long long*>(state + CH_PACKED), chain_pack(0u, 0u, true, it + 1));
             }
             return;
         }
@@ -1014,14 +1047,18 @@ __device__ __forceinline__ void chain_fused_body(const ChainRows& R, unsigned* s
         const int committed = min(sv * kSeg, nLive);
         if (threadIdx.x == 0)
         {
+            unsigned nj0 = (unsigned)j0, nm0 = m0;
+            bool     done = true;
             if (sv == 0) atomicExch(state + CH_ERROR, 3u), atomicExch(state + CH_DONE, 1u);  // cannot happen (segment 0 is always valid)
             else
             {
-                state[CH_J0] = (unsigned)(j0 + committed), state[CH_M0] = m0 + (unsigned)sAfter[sv - 1], state[CH_ITERS] = it + 1;
-                if (j0 + committed >= R.nU) state[CH_DONE] = 1u;
+                nj0 = (unsigned)(j0 + committed), nm0 = m0 + (unsigned)sAfter[sv - 1], done = j0 + committed >= R.nU;
+                // (read by the host and by k_peer_notify once the kernel has finished)
+                state[CH_J0] = nj0, state[CH_M0] = nm0, state[CH_ITERS] = it + 1;
+                if (done) state[CH_DONE] = 1u;
             }
-            __threadfence();
-            st_release_u32(state + CH_EPOCH, it + 1);
+            st_release_u64(reinterpret_cast<unsigned long long*>(state + CH_PACKED), chain_pack(nj0, nm0, done, it + 1));
+            sCtl[0] = (int)nj0, sCtl[1] = (int)nm0, sCtl[2] = done ? 1 : 0;  // this CTA's own next iteration
         }
         for (int t = threadIdx.x; t < committed; t += blockDim.x)
         {
@@ -1338,7 +1375,8 @@ static int ensure_checkpoints(fgl_ctx* c, SampleStream* s, long long wantCk)
 template <int K>
 static int build_table(fgl_ctx* c, SampleStream* s, DevBuf& table, unsigned long long rawBegin, unsigned long long need, unsigned long long* rawEndOut)
 {
-    if (int rc = fgl_reserve(c, table, (size_t)need * K * 4 + 16)) return rc;
+    if (int rc = fgl_not_while_recording(c, "building a sample table (render the frame once without recording first)")) return rc;
+    if (int rc = fgl_reserve(c, table, (size_t)need * (K == 3 ? 4 : K) * 4 + 16)) return rc;  // ball: x, y, z + the sample's SSAO scale
     if (int rc = fgl_reserve(c, s->counters, 64)) return rc;
     unsigned long long* dAcc = (unsigned long long*)s->counters.p;
     unsigned long long* dRawEnd = dAcc + 1;
@@ -1402,7 +1440,7 @@ int fgl_stream_prepare_ssao(fgl_ctx* c, SsaoPass& S)
         if (int rc = build_table<3>(c, s, s->ball, 0, need, &s->ballRawEnd)) return rc;
         s->ballNeed = need;
     }
-    S.ball = (const float*)s->ball.p;
+    S.ball = (const float4*)s->ball.p;
     s->ssaoThisFrame = true, s->ssaoSamples = need;
     return FGL_OK;
 }
@@ -1466,6 +1504,7 @@ static int launch_chain(fgl_ctx* c, SampleStream* s, ChainRows& R, int nU, size_
         }
         ready = true;
     }
+    if (nU >= (1 << kChainMaxRowsLog2)) return fgl_fail(c, FGL_ERR_UNSUPPORTED, "pcss chain: more than 2^27 uncertain pixels in one band");
     const int         regs = regsEnv ? regsEnv : (shared ? 40 : 64);
     const bool        coop = coopEnv >= 0 ? coopEnv != 0 : !shared;
     const ChainKernel kernel = regs <= 32 ? all[3] : regs <= 40 ? all[2] : regs <= 48 ? all[1] : all[0];
@@ -1542,6 +1581,8 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     ChainPass P;
     memset(&P, 0, sizeof P);
     P.sm = L.sm;
+    if (pcss)
+        if (int rc = fgl_not_while_recording(c, "a PCSS frame (its sample-stream chain reports counts to the host)")) return rc;
     if (!pcss)
     {
         if (phase == FGL_VIS_PREPARE || phase == FGL_VIS_LAUNCH) return FGL_OK;  // PCF offsets are closed-form: nothing depends on earlier bands

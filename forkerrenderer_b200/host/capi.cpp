@@ -6,6 +6,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "forkergl.h"
 #include "forkergl_b200.h"
@@ -30,6 +31,39 @@ static int Guard(F&& f)
         return 1;
     }
 }
+
+namespace
+{
+struct ReplayState
+{
+    enum { Cold, Warm, Recorded, Unsupported } state = Cold;
+    int                        frameId = -1;
+    std::vector<unsigned char> key;
+    std::string                why;
+};
+ReplayState s_Replay;
+
+std::vector<unsigned char> ReplayKey(const Scene& s, int shadow_mode, int materialize)
+{
+    std::vector<unsigned char> k;
+    auto put = [&](const void* p, size_t n) { k.insert(k.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+    const Scene* sp = &s;
+    put(&sp, sizeof sp), put(&shadow_mode, sizeof shadow_mode), put(&materialize, sizeof materialize);
+    const Vector3f eye = s.GetCamera().GetPosition();
+    const Matrix4x4f view = s.GetCamera().GetViewMatrix();
+    const PointLight& l = s.GetPointLight();
+    put(&eye, sizeof eye), put(&view, sizeof view), put(&l.position, sizeof l.position), put(&l.color, sizeof l.color);
+    const int misc[8] = { s.GetWidth(), s.GetHeight(), s.IsSSAAOn(), s.GetSSAAKernelSize(), s.IsSSAOOn(), (int)ForkerGL::GetRenderMode(),
+                          Shadow::GetShadowStatus(), (int)s.GetProjectionType() };
+    put(misc, sizeof misc);
+    for (unsigned i = 0; i < s.GetModelCount(); ++i)
+    {
+        const Matrix4x4f m = s.GetModelMatrix(i);
+        put(&m, sizeof m);
+    }
+    return k;
+}
+}  // namespace
 
 extern "C" {
 
@@ -79,7 +113,13 @@ int frh_scene_load(const char* assets_dir, const char* scene_file, int wrap, int
     });
 }
 
-void frh_scene_free(void* scene) { delete (Scene*)scene; }
+void frh_scene_free(void* scene)
+{
+    // a recording refers to this scene's device meshes and is keyed by its address: it goes with the scene
+    if (s_Replay.frameId >= 0) Guard([&] { fgl_frame_release(ForkerGL::Context(), s_Replay.frameId); });
+    s_Replay = ReplayState();
+    delete (Scene*)scene;
+}
 
 // info[0..7] = width, height, ssaa on, ssaa k, ssao on, deferred, shadow on, triangle count
 int frh_scene_info(void* scene, int* info)
@@ -127,6 +167,65 @@ int frh_render(void* scene, int shadow_mode, int materialize_frame_f32)
         Render::Render(*s);
     });
 }
+
+// Multi-frame use (SURVEY.md §8 f, N4; the reference's main renders one frame and exits, main.cpp:18-55): the frame as a
+// recorded CUDA graph (include/forkergl_b200.h "fgl_frame_*").  The first call renders eagerly (buffers and sample tables get
+// their sizes), the second records Render::Preconfigure + Render::Render and replays the recording, every further call is ONE
+// graph launch; after frh_set_camera / frh_set_point_light (or another shadow mode) the frame is recorded again and the graph
+// patched in place.  Frames that cannot be recorded (PCSS, forward mode with a stochastic filter, per-triangle submission,
+// a sort-first group) are rendered eagerly, every time.  *out_replayed: 1 if this call was a graph launch.
+
+int frh_render_replay(void* scene, int shadow_mode, int materialize_frame_f32, int* out_replayed)
+{
+    return Guard([&] {
+        Scene* s = (Scene*)scene;
+        if (out_replayed) *out_replayed = 0;
+        auto eager = [&] {
+            Shadow::SetShadowMode((Shadow::Mode)shadow_mode);
+            ForkerGL::Params().materialize_frame_f32 = materialize_frame_f32;
+            Render::Preconfigure(*s);
+            Render::Render(*s);
+        };
+        fgl_ctx* ctx = ForkerGL::Context();
+        std::vector<unsigned char> key = ReplayKey(*s, shadow_mode, materialize_frame_f32);
+        ReplayState& R = s_Replay;
+        if (R.state == ReplayState::Unsupported && key == R.key) return eager();
+        if (R.state == ReplayState::Cold || (R.state == ReplayState::Unsupported && key != R.key))
+        {   // sizes first; (an unsupported frame gets another chance when its parameters change, e.g. PCSS -> hard)
+            eager();
+            if (R.state == ReplayState::Cold) R.state = ReplayState::Warm;
+            else R.state = ReplayState::Warm, R.key.clear();
+            return;
+        }
+        if (!(R.state == ReplayState::Recorded && key == R.key))
+        {
+            ForkerGL::FlushTriangles();
+            ForkerGL::Check(fgl_frame_record_begin(ctx), "record begin");
+            bool ok = true;
+            try
+            {
+                eager();
+            }
+            catch (const std::exception& e)
+            {
+                ok = false, R.why = e.what();
+            }
+            if (ok && fgl_frame_record_end(ctx, &R.frameId) != FGL_OK) ok = false, R.why = fgl_last_error(ctx);
+            if (!ok)
+            {
+                fgl_frame_record_abort(ctx);
+                R.state = ReplayState::Unsupported, R.key = key;
+                return eager();
+            }
+            R.state = ReplayState::Recorded, R.key = key;
+        }
+        ForkerGL::Check(fgl_frame_replay(ctx, R.frameId), "replay");
+        ForkerGL::InvalidateHostMirrors();
+        if (out_replayed) *out_replayed = 1;
+    });
+}
+// why the last frh_render_replay fell back to eager rendering ("" if it did not)
+const char* frh_replay_fallback_reason() { return s_Replay.state == ReplayState::Unsupported ? s_Replay.why.c_str() : ""; }
 
 // The same frame in two calls (sort-first multi-GPU: the PCSS chain state is exchanged between them).
 int frh_render_begin(void* scene, int shadow_mode, int materialize_frame_f32)

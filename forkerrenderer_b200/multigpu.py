@@ -30,6 +30,11 @@ class FacadeRenderer:
     def finish(self):
         self.host.render_finish(self.scene)
 
+    def replay(self):
+        """The whole frame through frh_render_replay (a recorded CUDA graph where the frame allows it).  True = graph launch."""
+        self.fgl.set_row_band(0, -1)
+        return self.host.render_replay(self.scene, self.shadow_mode, self.materialize)
+
 
 class SyntheticRenderer:
     """A forkerrenderer_b200.synthetic.SyntheticScene through the raw C ABI."""

@@ -281,6 +281,33 @@ int fgl_host_free(fgl_ctx* ctx, void* ptr);
 int fgl_copy_plane_rows_to_device(fgl_ctx* ctx, int plane, int row_begin, int row_end, void* dst_device,
                                   size_t dst_bytes);
 
+/* ---- recorded frames: multi-frame use (SURVEY.md §8 f, N4; the reference's main is one-shot, src/main.cpp:18-55) ----------
+ * A frame whose passes need no host read-back is a fixed sequence of copies, clears and kernels on the ctx's stream: hard-shadow
+ * or PCF lighting, with or without SSAO, the blur and SSAA.  It can be recorded ONCE as a CUDA graph and replayed with one
+ * launch per frame.  Not recordable (FGL_ERR_UNSUPPORTED, the context stays usable): PCSS (its sample-stream chain reports
+ * counts to the host), forward mode with PCF / PCSS, fgl_draw_triangles, a context of a sort-first group.
+ *   fgl_frame_record_begin  every call on this context up to fgl_frame_record_end is recorded instead of executed — the usual
+ *                           frame sequence from fgl_begin_frame to fgl_draw_screen_space_pixels / fgl_ssaa_resolve.  The same
+ *                           frame (same buffer sizes, same scene) must have been rendered once before without recording:
+ *                           buffers and sample tables are sized then, nothing may allocate or wait for the device while
+ *                           recording.  Reads, uploads and fgl_sync are refused until the recording ends.
+ *   fgl_frame_record_end    *frame_id < 0: creates a replayable frame and stores its id; *frame_id >= 0: UPDATES that frame in
+ *                           place to the newly recorded parameters (a moved camera or light: same passes, other uniforms) —
+ *                           the graph is patched, not rebuilt, when its shape is unchanged.  The recorded frame has NOT been
+ *                           rendered yet: replay it before reading planes.
+ *   fgl_frame_record_abort  ends a recording without keeping anything (after an error inside the sequence)
+ *   fgl_frame_replay        enqueues the whole frame on the ctx's stream; planes are then read as after an eager frame
+ *   fgl_frame_info          number of graph nodes (kernels + copies + clears) and of kernel launches of one replay
+ *   fgl_frame_release       frees a recorded frame
+ * A recorded frame becomes invalid (fgl_frame_replay: FGL_ERR_STATE) when a device buffer it uses is re-allocated afterwards,
+ * e.g. by rendering a larger frame on the same context. */
+int fgl_frame_record_begin(fgl_ctx* ctx);
+int fgl_frame_record_end(fgl_ctx* ctx, int* frame_id);
+int fgl_frame_record_abort(fgl_ctx* ctx);
+int fgl_frame_replay(fgl_ctx* ctx, int frame_id);
+int fgl_frame_info(fgl_ctx* ctx, int frame_id, int* out_nodes, int* out_kernel_launches);
+int fgl_frame_release(fgl_ctx* ctx, int frame_id);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* Per-kernel CUDA-event timing.  When enabled every kernel launch is bracketed by events on the ctx stream;
  * fgl_get_timings returns, for the launches since the last fgl_reset_timings, up to `max` records. */

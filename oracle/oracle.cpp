@@ -1158,6 +1158,13 @@ int fgl_chain_peer_mailbox(fgl_ctx* c, void**, void*, size_t) { return fail(c, F
 int fgl_chain_peer_connect(fgl_ctx* c, void*, const void*, int, int enable) { return enable ? fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle has no peer memory") : FGL_OK; }
 int fgl_host_alloc(fgl_ctx*, size_t bytes, void** out) { if (!out) return FGL_ERR_INVALID; *out = malloc(bytes ? bytes : 16); return *out ? FGL_OK : FGL_ERR_INVALID; }
 int fgl_host_free(fgl_ctx*, void* p) { free(p); return FGL_OK; }
+// recorded frames are CUDA graphs: the oracle executes every call as it arrives and has nothing to replay
+int fgl_frame_record_begin(fgl_ctx* c) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle does not record frames"); }
+int fgl_frame_record_end(fgl_ctx* c, int*) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle does not record frames"); }
+int fgl_frame_record_abort(fgl_ctx*) { return FGL_OK; }
+int fgl_frame_replay(fgl_ctx* c, int) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle does not record frames"); }
+int fgl_frame_info(fgl_ctx* c, int, int*, int*) { return fail(c, FGL_ERR_UNSUPPORTED, "the CPU oracle does not record frames"); }
+int fgl_frame_release(fgl_ctx*, int) { return FGL_OK; }
 
 // oracle-only: number of mt19937 draws consumed since fgl_begin_frame (used by the stream-accounting tests)
 uint64_t orc_rng_draws(fgl_ctx* c) { return c->draws; }
