@@ -129,7 +129,7 @@ def test_raw_abi_record_replay_and_refusals():
         f.frame_record_begin()
         with pytest.raises(B.FglError) as e:
             s.render(320, 200, shadow_mode=B.SHADOW_PCSS, ssao=True)
-        assert "recorded frame" in str(e.value)
+        assert "record" in str(e.value)  # (whichever refusal comes first: the larger sample table, or the chain's read-backs)
         f.frame_record_abort()
         s.render(320, 200, shadow_mode=B.SHADOW_HARD, ssao=True)
         assert P.bits_equal(eager["frame"], f.read_plane("frame"))
