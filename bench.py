@@ -356,9 +356,12 @@ def run_ours(args):
     k2 = 4 if re.search(r"^ssaa\s+on", scene_txt, re.M) else 1
     stream_bytes = cfgd["width"] * cfgd["height"] * k2 * per_px // world
     small = stream_bytes < (512 << 20)
-    # default: two frames in flight on one GPU (the latency-bound PCSS chain of one frame runs next to the other frame's passes);
-    # in a group the chain's serial relay through the bands bounds the frame, a second frame in flight buys nothing (profiles/)
-    want = args.inflight if args.inflight > 0 else (2 if world == 1 else 1)
+    # default: frames in flight on one GPU (the latency-bound PCSS chain of one frame runs next to the other frames' passes, and a
+    # frame's read-back next to the others' kernels): three while three contexts' sample tables and planes (about 1.5 kB per pixel
+    # each) stay below a third of the HBM, else two; in a group the chain's serial relay through the bands bounds the frame, a
+    # second frame in flight buys nothing (profiles/)
+    ctx_bytes = cfgd["width"] * cfgd["height"] * k2 * 1500
+    want = args.inflight if args.inflight > 0 else ((3 if 3 * ctx_bytes < (60 << 30) else 2) if world == 1 else 1)
     inflight = 1 if (small or (world > 1 and args.group != "peer")) else want
 
     _dbg("process group up, building %d renderer instance(s)" % inflight)
@@ -545,7 +548,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=0,
                     help="frames rendered concurrently (each on its own facade instance / context / stream / host thread); 0 = default "
-                         "(2 on one GPU, 1 in a group); workloads small enough to need an L2 flush between frames always use 1")
+                         "(3 on one GPU up to 4K, 2 at 8K, 1 in a group); workloads small enough to need an L2 flush between frames always use 1")
     ap.add_argument("--replay", default="auto", choices=["auto", "off"],
                     help="auto: hard-shadow / PCF workloads on one GPU are rendered through frh_render_replay (the frame recorded once as a "
                          "CUDA graph, then one launch per frame); off: always the eager facade calls")

@@ -270,6 +270,10 @@ FGL_D float fgl_pow(float a, float b) { return powf(a, b); }
 // CUDA alike, so a zero base needs no evaluation — emissive colours are zero almost everywhere and background pixels are zero
 // in every channel, which makes this three to nine of a pixel's ten powf calls.
 FGL_D float fgl_pow_gamma(float a, float p) { return a == 0.f ? 0.f : powf(a, p); }
+// The Blinn-Phong highlight pow(max(0, N.H), shininess): pow(x, +-0) is 1 for every x and pow(+0, y > 0) is +0, again by
+// definition in both libraries — background pixels (shininess 0) and surfaces turned away from the highlight need no evaluation.
+// (+0 only: pow(-0, odd integer) is -0)
+FGL_D float fgl_pow_spec(float a, float p) { return p == 0.f ? 1.f : (__float_as_uint(a) == 0u && p > 0.f ? 0.f : powf(a, p)); }
 FGL_D V3    vpow(V3 v, float p) { return v3(fgl_pow_gamma(v.x, p), fgl_pow_gamma(v.y, p), fgl_pow_gamma(v.z, p)); }
 FGL_D V3    vclamp01(V3 v) { return v3(clampf(v.x, 0.f, 1.f), clampf(v.y, 0.f, 1.f), clampf(v.z, 0.f, 1.f)); }
 
@@ -287,7 +291,7 @@ FGL_D V3 blinn_phong_light(const LightConsts& lc, V3 lightDir, V3 halfwayDir, V3
     V3          dl = vpow(diffuseColor, kGamma), el = vpow(emissive, kGamma);
     float       ao = param.x, ks = param.y, shininess = param.z;
     float       diff = fmaxf(0.f, vdot(lightDir, normal));
-    float       spec = fgl_pow(fmaxf(0.f, vdot(halfwayDir, normal)), shininess);
+    float       spec = fgl_pow_spec(fmaxf(0.f, vdot(halfwayDir, normal)), shininess);
     V3          ambient = vscale(vmul(v3(0.3f, 0.3f, 0.3f), dl), ao);
     V3          diffuse = vscale(vscale(dl, diff), ao);
     V3          specular = vscale(v3(ks, ks, ks), spec);
