@@ -1227,48 +1227,89 @@ __device__ __forceinline__ float pcf_taps(const ShadowMapD& sm, float4 s, float 
 // The average blocker depth is an ORDERED fp32 sum over the blocking taps (shadow.cpp:78-84): the blocking lanes
 // scatter their depth to shared memory at their rank, every lane then adds the n values in order (broadcast 128-bit
 // reads) — 2-3 instructions per tap instead of a shuffle loop (most pixels with a blocker have all 32 taps blocked).
-__global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
-                                                        ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
+// The kernel is bound by memory latency, not bandwidth: list entry -> coordinate + chunk index -> samples -> shadow-map gather ->
+// (ordered sum) -> PCF gathers are five dependent round trips per pixel, and a warp issues in order.  The first three do not
+// depend on any arithmetic, so they are fetched ahead and interleaved with the two gather phases of the current pixel:
+//   (A) list entry two pixels ahead, coordinate + chunk index one pixel ahead     — issued, not used
+//   (B) current pixel: blocker search (one gather round trip), ordered sum, penumbra
+//   (C) the next pixel's 96 samples (their address, the chunk index, arrived during B) — issued, not used
+//   (D) current pixel: the 64 PCF taps (one gather round trip)
+// leaving two round trips per pixel on the critical path.
+__global__ void __launch_bounds__(256, 5) k_pcss_visibility(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
+                                                           ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
 {
     __shared__ __align__(16) float sDepth[8][32];
     const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned nb = *nBlockers, nWarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
-    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nWarps)
+    const unsigned kNone = 0xffffffffu;  // list entry of a pixel deep in shadow: visibility 0 already written (k_chunk_index)
+    unsigned       i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // pipeline registers: pixel i (coordinate and samples), pixel i + nWarps (list entry)
+    unsigned idx = i < nb ? blockerList[i] : kNone;
+    unsigned idxNext = i + nWarps < nb ? blockerList[i + nWarps] : kNone;
+    float4   s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2   d0 = make_float2(0.f, 0.f), d1 = d0, d2 = d0;
+    if (idx != kNone)
     {
-        unsigned idx = blockerList[i];
-        if (idx == 0xffffffffu) continue;  // deep in shadow: visibility 0 already written (k_chunk_index)
-        float4   s = sc4[idx];
-        size_t   first = (size_t)chunkOf[idx] * 32;
-        float2   d0 = __ldg(disk + first + lane), d1 = __ldg(disk + first + 32 + lane), d2 = __ldg(disk + first + 64 + lane);
-        float    ox = (float)((double)d0.x * fs), oy = (float)((double)d0.y * fs);
-        float    sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
-        bool     blocked = s.z > sampleDepth + s.w;
-        unsigned mask = __ballot_sync(0xffffffffu, blocked);
-        const int n = __popc(mask);
-        if (blocked) sDepth[wid][__popc(mask & ltMask)] = sampleDepth;
-        __syncwarp();
-        float sum = 0.f;
-        const float4* q = reinterpret_cast<const float4*>(sDepth[wid]);
+        s = sc4[idx];
+        const float2* p = disk + (size_t)chunkOf[idx] * 32 + lane;
+        d0 = p[0], d1 = p[32], d2 = p[64];
+    }
+    for (; i < nb; i += nWarps)
+    {
+        // (A)
+        const unsigned idxAfter = i + 2 * nWarps < nb ? blockerList[i + 2 * nWarps] : kNone;
+        float4         sNext = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned       chunkNext = 0u;
+        if (idxNext != kNone) sNext = sc4[idxNext], chunkNext = chunkOf[idxNext];
+        asm volatile("" ::: "memory");
+        // (B)
+        float dBlocker = 0.f;
+        if (idx != kNone)
+        {
+            float    ox = (float)((double)d0.x * fs), oy = (float)((double)d0.y * fs);
+            float    sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
+            bool     blocked = s.z > sampleDepth + s.w;
+            unsigned mask = __ballot_sync(0xffffffffu, blocked);
+            const int n = __popc(mask);
+            if (blocked) sDepth[wid][__popc(mask & ltMask)] = sampleDepth;
+            __syncwarp();
+            float sum = 0.f;
+            const float4* q = reinterpret_cast<const float4*>(sDepth[wid]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-        {
-            if (4 * k >= n) break;
-            float4 v = q[k];
-            sum += v.x;
-            if (4 * k + 1 < n) sum += v.y;
-            if (4 * k + 2 < n) sum += v.z;
-            if (4 * k + 3 < n) sum += v.w;
+            for (int k = 0; k < 8; ++k)
+            {
+                if (4 * k >= n) break;
+                float4 v = q[k];
+                sum += v.x;
+                if (4 * k + 1 < n) sum += v.y;
+                if (4 * k + 2 < n) sum += v.z;
+                if (4 * k + 3 < n) sum += v.w;
+            }
+            __syncwarp();
+            dBlocker = mask ? sum / (float)n : 0.f;
         }
-        __syncwarp();
-        float dBlocker = mask ? sum / (float)n : 0.f;
-        float v = 1.f;
-        if (!(dBlocker < 0.001f))  // (double)dBlocker < 0.001 (shadow.cpp:101): float(0.001) is the smallest float above 0.001
+        asm volatile("" ::: "memory");
+        // (C)
+        float2 e0 = make_float2(0.f, 0.f), e1 = e0, e2 = e0;
+        if (idxNext != kNone)
         {
-            float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
-            v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
+            const float2* p = disk + (size_t)chunkNext * 32 + lane;
+            e0 = p[0], e1 = p[32], e2 = p[64];
         }
-        if (lane == 0) vis[idx] = v;
+        asm volatile("" ::: "memory");
+        // (D)
+        if (idx != kNone)
+        {
+            float v = 1.f;
+            if (!(dBlocker < 0.001f))  // (double)dBlocker < 0.001 (shadow.cpp:101): float(0.001) is the smallest float above 0.001
+            {
+                float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
+                v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
+            }
+            if (lane == 0) vis[idx] = v;
+        }
+        idx = idxNext, idxNext = idxAfter, s = sNext, d0 = e0, d1 = e1, d2 = e2;
     }
 }
 
@@ -1837,7 +1878,13 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     {
         // bytes of the entries that are actually filtered (counted on the device by k_chunk_index): coordinate + chunk index + 96 samples + result
         LaunchScope ls(c, "pcss_visibility", 0, (const unsigned*)s->mState.p + CH_NFILTERED, 16 + 4 + 768 + 4);
-        k_pcss_visibility<<<c->numSMs * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
+        static int visBlocksPerSM = 0;  // persistent warps: exactly as many CTAs as are resident at once
+        if (!visBlocksPerSM)
+        {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&visBlocksPerSM, k_pcss_visibility, 256, 0) != cudaSuccess || visBlocksPerSM < 1) visBlocksPerSM = 4;
+            cudaGetLastError();
+        }
+        k_pcss_visibility<<<c->numSMs * visBlocksPerSM, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
                                                    chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, visB);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
