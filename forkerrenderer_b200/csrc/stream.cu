@@ -1196,7 +1196,6 @@ __device__ __forceinline__ bool chunk_index_pixel(size_t idx, size_t n, unsigned
                 }
             }
         }
-        blockerList[kpre[idx]] = entry;
         filtered = entry != 0xffffffffu;
     }
     vis[idx] = v;
@@ -1210,8 +1209,15 @@ __global__ void __launch_bounds__(256) k_chunk_index(size_t n, unsigned long lon
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool   filtered = false;
     if (idx < n) filtered = chunk_index_pixel(idx, n, base, kpre, hasB, chunkOf, vis, blockerList, nBlockers, D, kDev);
-    unsigned cnt = __popc(__ballot_sync(0xffffffffu, filtered));
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(nFiltered, cnt);
+    // the pixels that still need their 96 taps, as a DENSE list (a warp reserves its slots with one atomic; the order of the
+    // list is arbitrary, its entries are independent of one another)
+    const unsigned m = __ballot_sync(0xffffffffu, filtered);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned  slot = 0;
+    if (lane == 0) slot = atomicAdd(nFiltered, (unsigned)__popc(m));
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (filtered) blockerList[slot + __popc(m & ((1u << lane) - 1u))] = (unsigned)idx;
 }
 
 // shadow.cpp:47-63 for one pixel by one warp: 64 taps, two per lane; the sum of 1/64 steps is exact
@@ -1227,45 +1233,89 @@ __device__ __forceinline__ float pcf_taps(const ShadowMapD& sm, float4 s, float 
 // The average blocker depth is an ORDERED fp32 sum over the blocking taps (shadow.cpp:78-84): the blocking lanes
 // scatter their depth to shared memory at their rank, every lane then adds the n values in order (broadcast 128-bit
 // reads) — 2-3 instructions per tap instead of a shuffle loop (most pixels with a blocker have all 32 taps blocked).
-// The kernel is bound by memory latency, not bandwidth: list entry -> coordinate + chunk index -> samples -> shadow-map gather ->
-// (ordered sum) -> PCF gathers are five dependent round trips per pixel, and a warp issues in order.  The first three do not
-// depend on any arithmetic, so they are fetched ahead and interleaved with the two gather phases of the current pixel:
-//   (A) list entry two pixels ahead, coordinate + chunk index one pixel ahead     — issued, not used
-//   (B) current pixel: blocker search (one gather round trip), ordered sum, penumbra
-//   (C) the next pixel's 96 samples (their address, the chunk index, arrived during B) — issued, not used
-//   (D) current pixel: the 64 PCF taps (one gather round trip)
-// leaving two round trips per pixel on the critical path.
-__global__ void __launch_bounds__(256, 5) k_pcss_visibility(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
-                                                           ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
+__global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
+                                                        ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
 {
     __shared__ __align__(16) float sDepth[8][32];
     const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned nb = *nBlockers, nWarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
-    const unsigned kNone = 0xffffffffu;  // list entry of a pixel deep in shadow: visibility 0 already written (k_chunk_index)
-    unsigned       i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    // pipeline registers: pixel i (coordinate and samples), pixel i + nWarps (list entry)
-    unsigned idx = i < nb ? blockerList[i] : kNone;
-    unsigned idxNext = i + nWarps < nb ? blockerList[i + nWarps] : kNone;
-    float4   s = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2   d0 = make_float2(0.f, 0.f), d1 = d0, d2 = d0;
-    if (idx != kNone)
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nb; i += nWarps)
     {
-        s = sc4[idx];
+        unsigned idx = blockerList[i];  // (pixels deep in shadow are not on the list: visibility 0 already written by k_chunk_index)
+        float4   s = sc4[idx];
+        size_t   first = (size_t)chunkOf[idx] * 32;
+        float2   d0 = __ldg(disk + first + lane), d1 = __ldg(disk + first + 32 + lane), d2 = __ldg(disk + first + 64 + lane);
+        float    ox = (float)((double)d0.x * fs), oy = (float)((double)d0.y * fs);
+        float    sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
+        bool     blocked = s.z > sampleDepth + s.w;
+        unsigned mask = __ballot_sync(0xffffffffu, blocked);
+        const int n = __popc(mask);
+        if (blocked) sDepth[wid][__popc(mask & ltMask)] = sampleDepth;
+        __syncwarp();
+        float sum = 0.f;
+        const float4* q = reinterpret_cast<const float4*>(sDepth[wid]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            if (4 * k >= n) break;
+            float4 v = q[k];
+            sum += v.x;
+            if (4 * k + 1 < n) sum += v.y;
+            if (4 * k + 2 < n) sum += v.z;
+            if (4 * k + 3 < n) sum += v.w;
+        }
+        __syncwarp();
+        float dBlocker = mask ? sum / (float)n : 0.f;
+        float v = 1.f;
+        if (!(dBlocker < 0.001f))  // (double)dBlocker < 0.001 (shadow.cpp:101): float(0.001) is the smallest float above 0.001
+        {
+            float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
+            v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
+        }
+        if (lane == 0) vis[idx] = v;
+    }
+}
+
+// The same filter with the loads that do not depend on any arithmetic fetched ahead.  List entry -> coordinate + chunk index ->
+// samples -> shadow-map gather -> (ordered sum) -> PCF gathers are five dependent round trips per pixel and a warp issues in
+// order; the first three are interleaved with the two gather phases of the current pixel:
+//   (A) list entry two pixels ahead, coordinate + chunk index one pixel ahead     — issued, not used
+//   (B) current pixel: blocker search (one gather round trip), ordered sum, penumbra
+//   (C) the next pixel's 96 samples (their address, the chunk index, arrived during B) — issued, not used
+//   (D) current pixel: the 64 PCF taps (one gather round trip)
+// 40 registers: six CTAs per SM instead of eight.  (On the sparse list of an earlier version, where entries of pixels deep in
+// shadow were skipped one by one, the per-entry cost of the pipeline doubled the instruction count and the kernel was slower,
+// 0.36 -> 0.48 ms at C3, although its long-scoreboard stalls fell from 25.7 to 7.7 per issue — profiles/r02b_*.)
+__global__ void __launch_bounds__(256, 6) k_pcss_visibility_pipe(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
+                                                                ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
+{
+    __shared__ __align__(16) float sDepth[8][32];
+    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned nb = *nBlockers, nWarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    unsigned       i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nb) return;
+    // pipeline registers: pixel i (coordinate and samples), pixel i + nWarps (list entry)
+    unsigned idx = blockerList[i];
+    unsigned idxNext = i + nWarps < nb ? blockerList[i + nWarps] : 0u;
+    float4   s = sc4[idx];
+    float2   d0, d1, d2;
+    {
         const float2* p = disk + (size_t)chunkOf[idx] * 32 + lane;
         d0 = p[0], d1 = p[32], d2 = p[64];
     }
     for (; i < nb; i += nWarps)
     {
+        const bool more = i + nWarps < nb;
         // (A)
-        const unsigned idxAfter = i + 2 * nWarps < nb ? blockerList[i + 2 * nWarps] : kNone;
+        const unsigned idxAfter = i + 2 * nWarps < nb ? blockerList[i + 2 * nWarps] : 0u;
         float4         sNext = make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned       chunkNext = 0u;
-        if (idxNext != kNone) sNext = sc4[idxNext], chunkNext = chunkOf[idxNext];
+        if (more) sNext = sc4[idxNext], chunkNext = chunkOf[idxNext];
         asm volatile("" ::: "memory");
         // (B)
-        float dBlocker = 0.f;
-        if (idx != kNone)
+        float dBlocker;
         {
             float    ox = (float)((double)d0.x * fs), oy = (float)((double)d0.y * fs);
             float    sampleDepth = shadow_lookup(sm, s.x + ox, s.y + oy);
@@ -1292,23 +1342,20 @@ __global__ void __launch_bounds__(256, 5) k_pcss_visibility(const unsigned* bloc
         asm volatile("" ::: "memory");
         // (C)
         float2 e0 = make_float2(0.f, 0.f), e1 = e0, e2 = e0;
-        if (idxNext != kNone)
+        if (more)
         {
             const float2* p = disk + (size_t)chunkNext * 32 + lane;
             e0 = p[0], e1 = p[32], e2 = p[64];
         }
         asm volatile("" ::: "memory");
         // (D)
-        if (idx != kNone)
+        float v = 1.f;
+        if (!(dBlocker < 0.001f))  // (double)dBlocker < 0.001 (shadow.cpp:101): float(0.001) is the smallest float above 0.001
         {
-            float v = 1.f;
-            if (!(dBlocker < 0.001f))  // (double)dBlocker < 0.001 (shadow.cpp:101): float(0.001) is the smallest float above 0.001
-            {
-                float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
-                v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
-            }
-            if (lane == 0) vis[idx] = v;
+            float penumbra = (s.z - dBlocker) * areaLight / dBlocker;
+            v = pcf_taps(sm, s, (float)(pcfFilter * (double)penumbra), d1, d2);
         }
+        if (lane == 0) vis[idx] = v;
         idx = idxNext, idxNext = idxAfter, s = sNext, d0 = e0, d1 = e1, d2 = e2;
     }
 }
@@ -1878,14 +1925,14 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     {
         // bytes of the entries that are actually filtered (counted on the device by k_chunk_index): coordinate + chunk index + 96 samples + result
         LaunchScope ls(c, "pcss_visibility", 0, (const unsigned*)s->mState.p + CH_NFILTERED, 16 + 4 + 768 + 4);
-        static int visBlocksPerSM = 0;  // persistent warps: exactly as many CTAs as are resident at once
-        if (!visBlocksPerSM)
-        {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&visBlocksPerSM, k_pcss_visibility, 256, 0) != cudaSuccess || visBlocksPerSM < 1) visBlocksPerSM = 4;
-            cudaGetLastError();
-        }
-        k_pcss_visibility<<<c->numSMs * visBlocksPerSM, 256, 0, st>>>((const unsigned*)s->blockerList.p, (const unsigned*)s->mState.p + CH_NBLOCKERS, sc4In,
-                                                   chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter, L.areaLight, visB);
+        static const bool pipelined = !(getenv("FGL_VIS_PIPELINE") && atoi(getenv("FGL_VIS_PIPELINE")) == 0);
+        const unsigned*   nList = (const unsigned*)s->mState.p + CH_NFILTERED;  // the list is dense: its length is the number of filtered pixels
+        if (pipelined)
+            k_pcss_visibility_pipe<<<c->numSMs * 6, 256, 0, st>>>((const unsigned*)s->blockerList.p, nList, sc4In, chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter,
+                                                                 L.areaLight, visB);
+        else
+            k_pcss_visibility<<<c->numSMs * 8, 256, 0, st>>>((const unsigned*)s->blockerList.p, nList, sc4In, chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter,
+                                                            L.areaLight, visB);
     }
     L.chunkOf = (const unsigned*)s->chunkOf.p;
     // known on the host as soon as the chain kernel has finished — a sort-first driver can hand it to the next band while
