@@ -1284,9 +1284,10 @@ __global__ void __launch_bounds__(256) k_pcss_visibility(const unsigned* blocker
 //   (B) current pixel: blocker search (one gather round trip), ordered sum, penumbra
 //   (C) the next pixel's 96 samples (their address, the chunk index, arrived during B) — issued, not used
 //   (D) current pixel: the 64 PCF taps (one gather round trip)
-// 40 registers: six CTAs per SM instead of eight.  (On the sparse list of an earlier version, where entries of pixels deep in
-// shadow were skipped one by one, the per-entry cost of the pipeline doubled the instruction count and the kernel was slower,
-// 0.36 -> 0.48 ms at C3, although its long-scoreboard stalls fell from 25.7 to 7.7 per issue — profiles/r02b_*.)
+// 40 registers: six CTAs per SM instead of eight.  Selected by FGL_VIS_PIPELINE=1; NOT the default: on the dense list the plain
+// kernel above is the faster one (C3 0.186 vs 0.202 ms, C5 0.155 vs 0.168 ms): with the deep-shadow entries gone every warp has
+// real work queued behind it, the long-scoreboard stalls the fetch-ahead removes (25.7 -> 7.7 per issue, ncu) were already
+// covered by the other 63 warps of the SM, and its extra instructions and lower occupancy cost more than they save.
 __global__ void __launch_bounds__(256, 6) k_pcss_visibility_pipe(const unsigned* blockerList, const unsigned* nBlockers, const float4* sc4, const unsigned* chunkOf,
                                                                 ShadowMapD sm, const float2* disk, double fs, double pcfFilter, float areaLight, float* vis)
 {
@@ -1925,7 +1926,8 @@ int fgl_stream_site_visibility(fgl_ctx* c, LightPass& L, size_t nTotal, const fl
     {
         // bytes of the entries that are actually filtered (counted on the device by k_chunk_index): coordinate + chunk index + 96 samples + result
         LaunchScope ls(c, "pcss_visibility", 0, (const unsigned*)s->mState.p + CH_NFILTERED, 16 + 4 + 768 + 4);
-        static const bool pipelined = !(getenv("FGL_VIS_PIPELINE") && atoi(getenv("FGL_VIS_PIPELINE")) == 0);
+        // (the fetch-ahead variant is measured, not the default: 0.202 vs 0.186 ms at C3, 0.168 vs 0.155 ms at C5 — profiles/r02c_*)
+        static const bool pipelined = getenv("FGL_VIS_PIPELINE") && atoi(getenv("FGL_VIS_PIPELINE")) != 0;
         const unsigned*   nList = (const unsigned*)s->mState.p + CH_NFILTERED;  // the list is dense: its length is the number of filtered pixels
         if (pipelined)
             k_pcss_visibility_pipe<<<c->numSMs * 6, 256, 0, st>>>((const unsigned*)s->blockerList.p, nList, sc4In, chunkOfB, L.sm, L.disk, L.pcssFilter, L.pcfFilter,

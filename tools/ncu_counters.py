@@ -1,5 +1,5 @@
 """Merges the counters of an .ncu-rep into profiles/r02_ncu_counters.json (the file bench.py quotes in roofline.counters).
-usage: python tools/ncu_counters.py report.ncu-rep WORKLOAD SOURCE_NOTE
+usage: python tools/ncu_counters.py report.ncu-rep WORKLOAD SOURCE_NOTE [name,name,...]   (only these timing-record names)
 Kernels are matched by name to the names of the library's timing records (kernels[].name of a bench line)."""
 import csv
 import json
@@ -27,6 +27,7 @@ COLS = {"gpu__time_duration.sum": ("dur_us", {"ns": 1e-3, "us": 1, "ms": 1e3, "s
 
 def main():
     rep, workload, note = sys.argv[1], sys.argv[2], sys.argv[3]
+    only = set(sys.argv[4].split(",")) if len(sys.argv) > 4 else None
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -34,7 +35,7 @@ def main():
     for r in rows[2:]:
         kname = r[hdr.index("Kernel Name")]
         name = next((v for k, v in NAMES.items() if k in kname), None)
-        if not name:
+        if not name or (only and name not in only):
             continue
         d = {}
         for key, (field, scale) in COLS.items():
