@@ -200,15 +200,18 @@ int frh_render_replay(void* scene, int shadow_mode, int materialize_frame_f32, i
         if (!(R.state == ReplayState::Recorded && key == R.key))
         {
             ForkerGL::FlushTriangles();
-            ForkerGL::Check(fgl_frame_record_begin(ctx), "record begin");
-            bool ok = true;
-            try
+            bool ok = fgl_frame_record_begin(ctx) == FGL_OK;  // refused inside a sort-first group, with timing on, or by a back end without graphs
+            if (!ok) R.why = fgl_last_error(ctx);
+            if (ok)
             {
-                eager();
-            }
-            catch (const std::exception& e)
-            {
-                ok = false, R.why = e.what();
+                try
+                {
+                    eager();
+                }
+                catch (const std::exception& e)
+                {
+                    ok = false, R.why = e.what();
+                }
             }
             if (ok && fgl_frame_record_end(ctx, &R.frameId) != FGL_OK) ok = false, R.why = fgl_last_error(ctx);
             if (!ok)
