@@ -53,6 +53,12 @@ std::vector<unsigned char> ReplayKey(const Scene& s, int shadow_mode, int materi
     const Matrix4x4f view = s.GetCamera().GetViewMatrix();
     const PointLight& l = s.GetPointLight();
     put(&eye, sizeof eye), put(&view, sizeof view), put(&l.position, sizeof l.position), put(&l.color, sizeof l.color);
+    // the run-time constants pushed by Render::Render (fgl_set_params) are baked into a recording as kernel parameters
+    const FglParams& prm = ForkerGL::Params();
+    const double     pd[2] = { prm.pcf_filter_size, prm.pcss_blocker_filter_size };
+    const float      pf[7] = { prm.area_light_size, prm.shadow_bias_slope, prm.shadow_bias_min, prm.shadow_intensity, prm.ssao_radius,
+                               prm.ssao_range_check_radius, prm.ssao_bias };
+    put(pd, sizeof pd), put(pf, sizeof pf), put(&prm.ssao_range_check, sizeof prm.ssao_range_check);
     const int misc[8] = { s.GetWidth(), s.GetHeight(), s.IsSSAAOn(), s.GetSSAAKernelSize(), s.IsSSAOOn(), (int)ForkerGL::GetRenderMode(),
                           Shadow::GetShadowStatus(), (int)s.GetProjectionType() };
     put(misc, sizeof misc);

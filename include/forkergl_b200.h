@@ -300,7 +300,8 @@ int fgl_copy_plane_rows_to_device(fgl_ctx* ctx, int plane, int row_begin, int ro
  *   fgl_frame_info          number of graph nodes (kernels + copies + clears) and of kernel launches of one replay
  *   fgl_frame_release       frees a recorded frame
  * A recorded frame becomes invalid (fgl_frame_replay: FGL_ERR_STATE) when a device buffer it uses is re-allocated afterwards,
- * e.g. by rendering a larger frame on the same context. */
+ * e.g. by rendering a larger frame on the same context.  Everything the recorded calls passed by value — uniforms, FglParams,
+ * buffer sizes — is part of the recording: change it by recording again into the same id. */
 int fgl_frame_record_begin(fgl_ctx* ctx);
 int fgl_frame_record_end(fgl_ctx* ctx, int* frame_id);
 int fgl_frame_record_abort(fgl_ctx* ctx);
